@@ -1,0 +1,1122 @@
+// tk_api.cu -- C-ABI of libtensorkrylov_b200.so: handle, inputs, the device-resident solve loop.
+//
+// The loop body follows tensorkrylov! (src/tensor_krylov_method.jl:63-120) phase by phase:
+//   step_bases  : orthonormalize!(decomp, k) + update_rhs!            kernels (1)
+//   compress    : solve_compressed_system                            kernels (2) (3)
+//   residual    : residualnorm! + the convergence/breakdown decision  kernels (4)
+// All state stays in HBM; the host only enqueues launches and polls the device status word a
+// few iterations behind the GPU.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/tensorkrylov_b200.h"
+#include "tk_compress.cuh"
+#include "tk_host.h"
+#include "tk_krylov.cuh"
+
+namespace tk {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define TK_CUDA(call)                                                                                     \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return tk::set_error(TK_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define TK_TRY(call)            \
+    do {                        \
+        int rc__ = (call);      \
+        if (rc__ != 0) return rc__; \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// NCCL is only needed for world > 1: bind it lazily so a single-GPU process never loads it.
+// ---------------------------------------------------------------------------------------------
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_bind() {
+    if (g_nccl.lib) return 0;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return set_error(TK_ENCCL, "cannot load libnccl.so.2: %s", dlerror());
+#define TK_SYM(field, name)                                                            \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(lib, name));         \
+    if (!g_nccl.field) return set_error(TK_ENCCL, "libnccl has no symbol %s", name);
+    TK_SYM(GetUniqueId, "ncclGetUniqueId")
+    TK_SYM(CommInitRank, "ncclCommInitRank")
+    TK_SYM(CommDestroy, "ncclCommDestroy")
+    TK_SYM(AllGather, "ncclAllGather")
+    TK_SYM(Broadcast, "ncclBroadcast")
+    TK_SYM(GetErrorString, "ncclGetErrorString")
+#undef TK_SYM
+    g_nccl.lib = lib;
+    return 0;
+}
+
+#define TK_NCCL(call)                                                                              \
+    do {                                                                                           \
+        ncclResult_t r__ = (call);                                                                 \
+        if (r__ != ncclSuccess) return tk::set_error(TK_ENCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r__)); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// device buffer with RAII
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t count = 0;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        count = 0;
+    }
+    int alloc(size_t n, bool zero = true) {
+        release();
+        if (n == 0) n = 1;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return set_error(TK_ENOMEM, "cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+        }
+        count = n;
+        if (zero) {
+            e = cudaMemset(p, 0, n * sizeof(T));
+            if (e != cudaSuccess) return set_error(TK_ECUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+        }
+        return 0;
+    }
+};
+
+struct HostOp {
+    int type = OP_DIA;
+    int ndiag = 0;
+    int offs[MAX_DIAG] = {0};
+    long long ld = 0;
+    long long nnz = 0;
+    DevBuf<double> vals;   // diag / val / dense
+    DevBuf<int> rowptr, colidx;
+    double bytes_per_row() const {  // operator bytes streamed per row by one SpMV
+        if (type == OP_DIA) return 8.0 * ndiag;
+        if (type == OP_CSR) return ld > 0 ? (12.0 * nnz + 4.0 * (ld + 1)) / (double)ld : 0.0;
+        return 8.0 * (double)ld;
+    }
+};
+
+struct SchedEntry {
+    bool set = false;
+    double lambda_min = 0.0;
+    int t = 0;
+    size_t off = 0;  // into the alpha/omega pools
+};
+
+enum { TM_TTR = 0, TM_GRAM = 1, TM_MGS = 2, TM_EIG = 3, TM_ASM = 4, TM_COMBINE = 5, TM_KINDS = 6 };
+
+}  // namespace tk
+
+using namespace tk;
+
+struct tk_handle {
+    int d = 0, dl = 0, first = 0, nmax = 0, ncol = 0, n = 0;
+    int instance = 0, matrixclass = 0, variant = 0, flags = 0, device = 0, rank = 0, world = 1;
+    long long ldv = 0;
+    int per_mode = 0, ncls = 1;
+    int chunk_modes = 16, nchunks = 1, chunk_base = 0;
+    cudaStream_t stream = nullptr;
+    ncclComm_t comm = nullptr;
+
+    // Krylov state
+    DevBuf<double> V, b, T, Hd, bt, g, S, orthS, bnorm2, vscratch, Tq;
+    DevBuf<int> fallbacks, mode_op_d, status_d, term_k_d, eigfail_d;
+    DevBuf<long long> niter_d;
+    DevBuf<OpDesc> ops_d;
+    std::vector<std::unique_ptr<HostOp>> ops;
+    std::vector<int> mode_op;   // local mode -> op index (-1 unset)
+    std::vector<char> rhs_set;
+    bool ops_dirty = true;
+
+    // schedule
+    std::vector<SchedEntry> sched;
+    std::vector<double> alpha_pool, omega_pool;
+    DevBuf<double> alpha_d, omega_d;
+    bool sched_dirty = true;
+    int tmax = 0;
+
+    // compressed solve / residual
+    DevBuf<double> theta, Q, Y, Z, E, bbm, partials, gathered, bnorm_d, relres_d, projres_d, orth_d, detail_d;
+    int ldq = 0;
+    long long ystride = 0, estride = 0, pstride_max = 0;
+    bool work_ready = false;
+    int last_k = 0, last_t = 0, last_tld = 0;
+    double last_lam_inv = 0.0;
+    bool begun = false;
+
+    // status polling
+    int* status_ring = nullptr;  // pinned
+    std::vector<cudaEvent_t> ring_ev;
+
+    // timing
+    struct Timed { int kind; cudaEvent_t a, b; double bytes; };
+    std::vector<Timed> timed;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    double tm_ms[TM_KINDS] = {0}, tm_bytes[TM_KINDS] = {0};
+    long long tm_launches[TM_KINDS] = {0};
+    long long launches = 0;
+
+    KrylovParams kp() const {
+        KrylovParams p;
+        p.n = n; p.ncol = ncol; p.ldv = ldv; p.vstride = (long long)ncol * ldv;
+        p.V = V.p; p.b = b.p; p.T = T.p; p.Hd = Hd.p; p.bt = bt.p; p.g = g.p; p.S = S.p; p.orthS = orthS.p;
+        p.fallbacks = fallbacks.p; p.ops = ops_d.p; p.mode_op = mode_op_d.p; p.status = status_d.p;
+        p.mode0_local = (first == 0 && dl > 0) ? 0 : -1;
+        return p;
+    }
+};
+
+namespace tk {
+
+static int check_mode(const tk_handle* h, int s, bool* local) {
+    if (!h) return set_error(TK_EINVAL, "null handle");
+    if (s < 0 || s >= h->d) return set_error(TK_EINVAL, "mode %d out of range [0,%d)", s, h->d);
+    *local = (s >= h->first && s < h->first + h->dl);
+    return 0;
+}
+
+static cudaEvent_t next_event(tk_handle* h) {
+    if (h->ev_used == h->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->ev_pool.push_back(e);
+    }
+    return h->ev_pool[h->ev_used++];
+}
+
+struct TimedScope {
+    tk_handle* h; int kind; cudaEvent_t a = nullptr; double bytes;
+    TimedScope(tk_handle* h_, int kind_, double bytes_) : h(h_), kind(kind_), bytes(bytes_) {
+        if (h->flags & TK_FLAG_TIME_KERNELS) { a = next_event(h); cudaEventRecord(a, h->stream); }
+    }
+    ~TimedScope() {
+        if (a) { cudaEvent_t b = next_event(h); cudaEventRecord(b, h->stream); h->timed.push_back({kind, a, b, bytes}); }
+    }
+};
+
+static int upload_ops(tk_handle* h) {
+    if (!h->ops_dirty) return 0;
+    for (int s = 0; s < h->dl; ++s)
+        if (h->mode_op[s] < 0) return set_error(TK_ESTATE, "operator of mode %d not set", h->first + s);
+    std::vector<OpDesc> descs(h->ops.size());
+    for (size_t i = 0; i < h->ops.size(); ++i) {
+        const HostOp& o = *h->ops[i];
+        OpDesc& dsc = descs[i];
+        std::memset(&dsc, 0, sizeof(dsc));
+        dsc.type = o.type; dsc.ndiag = o.ndiag; dsc.ld = o.ld;
+        std::memcpy(dsc.offs, o.offs, sizeof(o.offs));
+        dsc.diag = o.type == OP_DIA ? o.vals.p : nullptr;
+        dsc.val = o.type == OP_CSR ? o.vals.p : nullptr;
+        dsc.dense = o.type == OP_DENSE ? o.vals.p : nullptr;
+        dsc.rowptr = o.rowptr.p; dsc.colidx = o.colidx.p;
+    }
+    TK_TRY(h->ops_d.alloc(std::max<size_t>(descs.size(), 1), false));
+    TK_CUDA(cudaMemcpy(h->ops_d.p, descs.data(), descs.size() * sizeof(OpDesc), cudaMemcpyHostToDevice));
+    TK_CUDA(cudaMemcpy(h->mode_op_d.p, h->mode_op.data(), h->dl * sizeof(int), cudaMemcpyHostToDevice));
+    h->ops_dirty = false;
+    return 0;
+}
+
+static int upload_schedule(tk_handle* h) {
+    if (!h->sched_dirty) return 0;
+    int tmax = 0;
+    for (int k = 2; k <= h->nmax; ++k) {
+        if (!h->sched[k].set) return set_error(TK_ESTATE, "schedule entry k=%d not set (tk_set_schedule)", k);
+        tmax = std::max(tmax, h->sched[k].t);
+    }
+    TK_TRY(h->alpha_d.alloc(std::max<size_t>(h->alpha_pool.size(), 1), false));
+    TK_TRY(h->omega_d.alloc(std::max<size_t>(h->omega_pool.size(), 1), false));
+    TK_CUDA(cudaMemcpy(h->alpha_d.p, h->alpha_pool.data(), 8 * h->alpha_pool.size(), cudaMemcpyHostToDevice));
+    TK_CUDA(cudaMemcpy(h->omega_d.p, h->omega_pool.data(), 8 * h->omega_pool.size(), cudaMemcpyHostToDevice));
+    if (tmax != h->tmax) h->work_ready = false;
+    h->tmax = tmax;
+    h->sched_dirty = false;
+    return 0;
+}
+
+static int alloc_work(tk_handle* h) {
+    if (h->work_ready) return 0;
+    const int kmax = h->nmax, tmax = std::max(h->tmax, 1);
+    const int tld = (tmax + 3) & ~3;
+    h->ldq = (h->ncol + 1) & ~1;
+    TK_TRY(h->theta.alloc((size_t)h->ncls * h->ncol));
+    TK_TRY(h->Q.alloc((size_t)h->ncls * h->ldq * h->ldq));
+    h->ystride = (long long)kmax * tld;
+    TK_TRY(h->Y.alloc((size_t)h->dl * h->ystride));
+    TK_TRY(h->Z.alloc((size_t)h->dl * h->ystride));
+    h->estride = 3LL * tmax * tmax;
+    TK_TRY(h->E.alloc((size_t)h->dl * h->estride));
+    TK_TRY(h->bbm.alloc(h->dl));
+    h->pstride_max = 5LL * tmax * tmax + 2LL * tmax + 8;
+    TK_TRY(h->partials.alloc((size_t)h->nchunks * h->pstride_max));
+    if (h->world > 1) TK_TRY(h->gathered.alloc((size_t)h->world * h->nchunks * h->pstride_max));
+    h->work_ready = true;
+    return 0;
+}
+
+static size_t smem_limit(const tk_handle* h) {
+    (void)h;
+    return 200 * 1024;
+}
+
+template <typename K>
+static int allow_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) TK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+// --- kernel (1) launches -------------------------------------------------------------------
+static double op_bytes_per_row(const tk_handle* h) {
+    double acc = 0.0;
+    for (int s = 0; s < h->dl; ++s) acc += h->ops[h->mode_op[s]]->bytes_per_row();
+    return h->dl ? acc / h->dl : 0.0;
+}
+
+template <int CPM>
+static int launch_ttr_t(tk_handle* h, int k, int threads, size_t smem) {
+    TK_TRY(allow_smem(lanczos_ttr_kernel<CPM>, smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(h->dl * CPM);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CPM; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CPM > 1 ? 1 : 0;
+    KrylovParams p = h->kp();
+    TK_CUDA(cudaLaunchKernelEx(&cfg, lanczos_ttr_kernel<CPM>, p, k));
+    h->launches++;
+    return 0;
+}
+
+static int launch_ttr(tk_handle* h, int k) {
+    // split a mode over a cluster when there are too few modes to fill 148 SMs, or the slice would not fit in smem
+    int cpm = 1;
+    while (cpm < 8 && ((long long)h->dl * cpm < 296 || (size_t)h->n * 8 / cpm > smem_limit(h)) && h->n / (cpm * 2) >= 256) cpm *= 2;
+    const int chunk = (((h->n + cpm - 1) / cpm) + 1) & ~1;
+    const size_t smem = (size_t)chunk * 8;
+    if (smem > smem_limit(h)) return set_error(TK_EUNSUPPORTED, "n = %d is too large for the 3-term step kernel", h->n);
+    const int threads = chunk >= 2048 ? 512 : 256;
+    const double bytes = (op_bytes_per_row(h) + 32.0) * (double)h->n * h->dl;
+    TimedScope ts(h, TM_TTR, bytes);
+    switch (cpm) {
+        case 1: return launch_ttr_t<1>(h, k, threads, smem);
+        case 2: return launch_ttr_t<2>(h, k, threads, smem);
+        case 4: return launch_ttr_t<4>(h, k, threads, smem);
+        default: return launch_ttr_t<8>(h, k, threads, smem);
+    }
+}
+
+// Gram row of the newest column for `nmodes` modes starting at local mode `base`
+static int launch_gram(tk_handle* h, int ncols, int base, int nmodes) {
+    if (nmodes <= 0) return 0;
+    const bool w_smem = (size_t)h->n * 8 <= 160 * 1024;
+    // enough CTAs to fill the machine twice over, at most 16 columns per CTA, columns spread evenly
+    long long want = ((long long)ncols * nmodes + 591) / 592;
+    int cpc = (int)std::min<long long>(16, std::max<long long>(1, want));
+    int nchunks = (ncols + cpc - 1) / cpc;
+    cpc = (ncols + nchunks - 1) / nchunks;
+    const size_t smem = w_smem ? (size_t)h->n * 8 : 0;
+    TK_TRY(allow_smem(gram_row_kernel, smem));
+    const double bytes = 8.0 * (double)h->n * (double)ncols * nmodes;
+    TimedScope ts(h, TM_GRAM, bytes);
+    gram_row_kernel<<<dim3(nchunks, nmodes), 256, smem, h->stream>>>(h->kp(), ncols, cpc, base, w_smem ? 1 : 0);
+    h->launches++;
+    TK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int mgs_smem(tk_handle* h, size_t* smem, double** vscr) {
+    size_t need = ((size_t)h->ncol + (size_t)h->n) * 8;
+    if (need <= smem_limit(h)) {
+        *smem = need; *vscr = nullptr;
+    } else {
+        if (!h->vscratch.p) TK_TRY(h->vscratch.alloc((size_t)h->dl * h->ldv));
+        *smem = (size_t)h->ncol * 8; *vscr = h->vscratch.p;
+    }
+    return 0;
+}
+
+static int launch_monitor(tk_handle* h, int newcol, int base, int nmodes, int reorth) {
+    if (nmodes <= 0) return 0;
+    size_t smem; double* vscr;
+    TK_TRY(mgs_smem(h, &smem, &vscr));
+    if (!reorth) { smem = 0; }
+    TK_TRY(allow_smem(monitor_kernel, smem));
+    monitor_kernel<<<nmodes, 512, smem, h->stream>>>(h->kp(), newcol, base, reorth, vscr);
+    h->launches++;
+    TK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int launch_arnoldi(tk_handle* h, int k) {
+    size_t smem; double* vscr;
+    TK_TRY(mgs_smem(h, &smem, &vscr));
+    TK_TRY(allow_smem(arnoldi_mgs_kernel, smem));
+    const double bytes = (16.0 * k + op_bytes_per_row(h) + 24.0) * (double)h->n * h->dl;
+    TimedScope ts(h, TM_MGS, bytes);
+    arnoldi_mgs_kernel<<<h->dl, 512, smem, h->stream>>>(h->kp(), k, vscr);
+    h->launches++;
+    TK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// orthonormalize!(decomp, k) for every local mode + update_rhs!   (orthogonal_bases.jl:162-180, utils.jl:466-476)
+static int enqueue_step_bases(tk_handle* h, int k) {
+    const int mode0 = (h->first == 0 && h->dl > 0) ? 1 : 0;
+    if (h->variant == TK_ARNOLDI) {
+        TK_TRY(launch_arnoldi(h, k));
+        TK_TRY(launch_gram(h, k + 1, 0, mode0));
+        TK_TRY(launch_monitor(h, k, 0, mode0, 0));
+    } else {
+        TK_TRY(launch_ttr(h, k));
+        if (h->variant == TK_LANCZOS_REORTH) {
+            TK_TRY(launch_gram(h, k + 1, 0, h->dl));
+            TK_TRY(launch_monitor(h, k, 0, h->dl, 1));
+        } else {
+            TK_TRY(launch_gram(h, k + 1, 0, mode0));
+            TK_TRY(launch_monitor(h, k, 0, mode0, 0));
+        }
+    }
+    return 0;
+}
+
+static int launch_eig(const double* T, long long tstride, int ncol, int k, int nprob, double* theta,
+                      int thstride, double* Q, long long qstride, int ldq, const int* status, int* fail, cudaStream_t st) {
+    const int threads = std::min(1024, ((k + 31) / 32) * 32);
+    if (k > 1024) return set_error(TK_EUNSUPPORTED, "eigensolver supports k <= 1024");
+    const int nwarp = threads / 32;
+    size_t base = (size_t)nwarp * 2 * k * 8;
+    size_t full = base + (size_t)k * (k | 1) * 8;
+    const bool q_smem = full <= 200 * 1024;
+    const size_t smem = q_smem ? full : base;
+    TK_TRY(allow_smem(tridiag_eig_kernel, smem));
+    tridiag_eig_kernel<<<nprob, threads, smem, st>>>(T, tstride, ncol, k, theta, thstride, Q, qstride, ldq, q_smem ? 1 : 0, status, fail);
+    TK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static CompressParams make_cp(tk_handle* h, int k) {
+    const SchedEntry& se = h->sched[k];
+    CompressParams c;
+    c.k = k; c.t = se.t; c.tld = (se.t + 3) & ~3; c.ncol = h->ncol;
+    c.per_mode = h->per_mode;
+    c.theta = h->theta.p; c.thstride = h->ncol;
+    c.Q = h->Q.p; c.qstride = (long long)h->ldq * h->ldq; c.ldq = h->ldq;
+    c.bt = h->bt.p;
+    c.alpha = h->alpha_d.p + se.off; c.omega = h->omega_d.p + se.off;
+    c.lam_inv = 1.0 / se.lambda_min;
+    c.Y = h->Y.p; c.Z = h->Z.p; c.ystride = h->ystride;
+    c.T = h->T.p; c.Hd = h->Hd.p;
+    c.E = h->E.p; c.estride = h->estride;
+    c.bb = h->bbm.p;
+    c.status = h->status_d.p;
+    return c;
+}
+
+// solve_compressed_system (tensor_krylov_method.jl:10-34)
+static int enqueue_compress(tk_handle* h, int k) {
+    if (h->instance == TK_NONSYM)
+        return set_error(TK_EUNSUPPORTED, "NonSymInstance compressed solve (Hessenberg exponential) is not implemented yet");
+    const double* Tsrc = h->T.p;
+    long long tstride = 3LL * h->ncol;
+    if (!h->per_mode && h->world > 1) {
+        // the reference exponentiates H_1 for every mode: ship mode 1's tridiagonal to all ranks
+        TK_NCCL(g_nccl.Broadcast(h->T.p, h->Tq.p, 3 * (size_t)h->ncol, ncclDouble, 0, h->comm, h->stream));
+        Tsrc = h->Tq.p;
+    }
+    {
+        TimedScope ts(h, TM_EIG, 0.0);
+        TK_TRY(launch_eig(Tsrc, tstride, h->ncol, k, h->ncls, h->theta.p, h->ncol, h->Q.p, (long long)h->ldq * h->ldq,
+                          h->ldq, h->status_d.p, h->eigfail_d.p, h->stream));
+        h->launches++;
+    }
+    CompressParams c = make_cp(h, k);
+    const size_t smem = ((size_t)2 * k + (size_t)k * ASM_TJ) * 8;
+    TK_TRY(allow_smem(assemble_cp_kernel, smem));
+    {
+        TimedScope ts(h, TM_ASM, 0.0);
+        assemble_cp_kernel<<<h->dl, 256, smem, h->stream>>>(c);
+        h->launches++;
+        TK_CUDA(cudaGetLastError());
+    }
+    h->last_k = k; h->last_t = c.t; h->last_tld = c.tld; h->last_lam_inv = c.lam_inv;
+    return 0;
+}
+
+// residualnorm! (utils.jl:402-443) + exits of the loop body (tensor_krylov_method.jl:85-118)
+static int enqueue_residual(tk_handle* h, int k, double tol) {
+    CompressParams c = make_cp(h, k);
+    {
+        TimedScope ts(h, TM_ASM, 0.0);
+        gram_blocks_kernel<<<h->dl, 256, 0, h->stream>>>(c);
+        h->launches++;
+        TK_CUDA(cudaGetLastError());
+    }
+    const long long pst = 5LL * c.t * c.t + 2LL * c.t + 8;
+    TimedScope ts(h, TM_COMBINE, 0.0);
+    combine_chunk_kernel<<<h->nchunks, 256, 0, h->stream>>>(c, h->dl, h->chunk_modes, h->chunk_base, h->partials.p, pst,
+                                                            h->orthS.p, (h->first == 0 && h->dl > 0) ? 0 : -1);
+    h->launches++;
+    TK_CUDA(cudaGetLastError());
+    const double* parts = h->partials.p;
+    int nparts = h->nchunks;
+    if (h->world > 1) {
+        TK_NCCL(g_nccl.AllGather(h->partials.p, h->gathered.p, (size_t)h->nchunks * pst, ncclDouble, h->comm, h->stream));
+        parts = h->gathered.p;
+        nparts = h->nchunks * h->world;
+    }
+    FinalizeParams f;
+    f.k = k; f.t = c.t; f.nmax = h->nmax; f.nparts = nparts;
+    f.fixed_iterations = (h->flags & TK_FLAG_FIXED_ITERATIONS) ? 1 : 0;
+    f.pstride = pst; f.partials = parts; f.omega = c.omega;
+    f.lam_inv = c.lam_inv; f.lambda_min = h->sched[k].lambda_min; f.tol = tol;
+    f.bnorm = h->bnorm_d.p;
+    f.relres = h->relres_d.p; f.projres = h->projres_d.p; f.orth = h->orth_d.p; f.detail = h->detail_d.p;
+    f.status = h->status_d.p; f.niter = h->niter_d.p; f.term_k = h->term_k_d.p;
+    finalize_kernel<<<1, 256, 0, h->stream>>>(f);
+    h->launches++;
+    TK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int reset_state(tk_handle* h) {
+    TK_TRY(upload_ops(h));
+    for (int s = 0; s < h->dl; ++s)
+        if (!h->rhs_set[s]) return set_error(TK_ESTATE, "right-hand side of mode %d not set", h->first + s);
+    const int run = ST_RUNNING, zero = 0;
+    const long long nit = h->nmax;
+    TK_CUDA(cudaMemcpyAsync(h->status_d.p, &run, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    TK_CUDA(cudaMemcpyAsync(h->term_k_d.p, &zero, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    TK_CUDA(cudaMemcpyAsync(h->eigfail_d.p, &zero, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    TK_CUDA(cudaMemcpyAsync(h->niter_d.p, &nit, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    std::vector<double> ones(h->nmax, 1.0);   // ConvergenceData(nmax): ones (convergence.jl:11-20)
+    TK_CUDA(cudaMemcpyAsync(h->relres_d.p, ones.data(), 8 * (size_t)h->nmax, cudaMemcpyHostToDevice, h->stream));
+    TK_CUDA(cudaMemcpyAsync(h->projres_d.p, ones.data(), 8 * (size_t)h->nmax, cudaMemcpyHostToDevice, h->stream));
+    TK_CUDA(cudaMemcpyAsync(h->orth_d.p, ones.data(), 8 * (size_t)h->nmax, cudaMemcpyHostToDevice, h->stream));
+    TK_CUDA(cudaMemsetAsync(h->T.p, 0, 8 * h->T.count, h->stream));
+    TK_CUDA(cudaMemsetAsync(h->bt.p, 0, 8 * h->bt.count, h->stream));
+    TK_CUDA(cudaMemsetAsync(h->detail_d.p, 0, 8 * h->detail_d.count, h->stream));
+    if (h->Hd.p) TK_CUDA(cudaMemsetAsync(h->Hd.p, 0, 8 * h->Hd.count, h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    h->ev_used = 0;
+    h->timed.clear();
+    h->launches = 0;
+    for (int i = 0; i < TM_KINDS; ++i) { h->tm_ms[i] = 0; h->tm_bytes[i] = 0; h->tm_launches[i] = 0; }
+    return 0;
+}
+
+// orthonormalize!(decomp, b), initialize_compressed_rhs, kronprodnorm   (tensor_krylov_method.jl:48-55)
+static int begin_solve(tk_handle* h) {
+    TK_TRY(reset_state(h));
+    if (h->dl > 0) {
+        init_basis_kernel<<<h->dl, 512, 0, h->stream>>>(h->kp(), h->bnorm2.p);
+        h->launches++;
+        TK_CUDA(cudaGetLastError());
+    }
+    // b_norm = sqrt(prod_s b_s.b_s) over ALL modes, in mode order
+    std::vector<double> bn2(std::max(h->dl, 1));
+    TK_CUDA(cudaMemcpyAsync(bn2.data(), h->bnorm2.p, 8 * (size_t)h->dl, cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    double prod = 1.0;
+    for (int s = 0; s < h->dl; ++s) prod *= bn2[s];
+    if (h->world > 1) {
+        DevBuf<double> tmp;
+        TK_TRY(tmp.alloc(h->world + 1));
+        TK_CUDA(cudaMemcpyAsync(tmp.p + h->world, &prod, 8, cudaMemcpyHostToDevice, h->stream));
+        TK_NCCL(g_nccl.AllGather(tmp.p + h->world, tmp.p, 1, ncclDouble, h->comm, h->stream));
+        std::vector<double> all(h->world);
+        TK_CUDA(cudaMemcpyAsync(all.data(), tmp.p, 8 * (size_t)h->world, cudaMemcpyDeviceToHost, h->stream));
+        TK_CUDA(cudaStreamSynchronize(h->stream));
+        prod = 1.0;
+        for (int r = 0; r < h->world; ++r) prod *= all[r];
+    }
+    const double bnorm = std::sqrt(prod);
+    TK_CUDA(cudaMemcpyAsync(h->bnorm_d.p, &bnorm, 8, cudaMemcpyHostToDevice, h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    // Gram "row" of column 1 starts the orthogonality bookkeeping, then step k = 1
+    const int mode0 = (h->first == 0 && h->dl > 0) ? 1 : 0;
+    const int nmon = h->variant == TK_LANCZOS_REORTH ? h->dl : mode0;
+    TK_TRY(launch_gram(h, 1, 0, nmon));
+    TK_TRY(launch_monitor(h, 0, 0, nmon, 0));
+    TK_TRY(enqueue_step_bases(h, 1));
+    h->begun = true;
+    return 0;
+}
+
+static int collect_timing(tk_handle* h) {
+    for (auto& t : h->timed) {
+        float ms = 0.f;
+        TK_CUDA(cudaEventElapsedTime(&ms, t.a, t.b));
+        h->tm_ms[t.kind] += ms;
+        h->tm_bytes[t.kind] += t.bytes;
+        h->tm_launches[t.kind] += 1;
+    }
+    h->timed.clear();
+    return 0;
+}
+
+}  // namespace tk
+
+// =============================================================================================
+extern "C" {
+
+const char* tk_last_error(void) { return tk::g_err; }
+int tk_version(void) { return 100; }
+
+int tk_device_count(int* count) {
+    if (!count) return set_error(TK_EINVAL, "null count");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) { *count = 0; return set_error(TK_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    return 0;
+}
+
+int tk_comm_unique_id(void* out128) {
+    if (!out128) return set_error(TK_EINVAL, "null buffer");
+    TK_TRY(nccl_bind());
+    ncclUniqueId id;
+    TK_NCCL(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(out128, &id, 128);
+    return 0;
+}
+
+int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_t instance, int32_t matrixclass,
+              int32_t variant, int32_t flags, int32_t device, int32_t rank, int32_t world, const void* unique_id) {
+    if (!out || !n) return set_error(TK_EINVAL, "null argument");
+    *out = nullptr;
+    if (d < 1 || nmax < 1) return set_error(TK_EINVAL, "need d >= 1 and nmax >= 1");
+    for (int s = 1; s < d; ++s)
+        if (n[s] != n[0]) return set_error(TK_EUNSUPPORTED, "all modes must have the same order (n[%d]=%lld, n[0]=%lld)", s, (long long)n[s], (long long)n[0]);
+    if (n[0] < 1 || n[0] > (1 << 30)) return set_error(TK_EINVAL, "bad order n = %lld", (long long)n[0]);
+    if (nmax > n[0]) return set_error(TK_EINVAL, "nmax = %d exceeds n = %lld", nmax, (long long)n[0]);
+    if (instance != TK_SYM && instance != TK_NONSYM) return set_error(TK_EINVAL, "bad instance %d", instance);
+    if (variant < TK_LANCZOS || variant > TK_ARNOLDI) return set_error(TK_EINVAL, "bad variant %d", variant);
+    if (matrixclass < 0 || matrixclass > TK_GENERIC) return set_error(TK_EINVAL, "bad matrix class %d", matrixclass);
+    if (world < 1 || rank < 0 || rank >= world) return set_error(TK_EINVAL, "bad rank/world %d/%d", rank, world);
+    if (world > 1 && !unique_id) return set_error(TK_EINVAL, "world > 1 needs the NCCL unique id");
+    int ndev = 0;
+    TK_TRY(tk_device_count(&ndev));
+    if (device < 0 || device >= ndev) return set_error(TK_ECUDA, "CUDA device %d not available (%d visible)", device, ndev);
+    TK_CUDA(cudaSetDevice(device));
+
+    std::unique_ptr<tk_handle> h(new tk_handle());
+    h->d = d; h->n = (int)n[0]; h->nmax = nmax; h->ncol = nmax + 1;
+    h->instance = instance; h->matrixclass = matrixclass; h->variant = variant; h->flags = flags;
+    h->device = device; h->rank = rank; h->world = world;
+    h->ldv = ((long long)h->n + 15) & ~15LL;
+    // block partition of the modes, aligned to combine chunks so the product order does not depend on world
+    const int mc = h->chunk_modes;
+    int per = (d + world - 1) / world;
+    if (d >= world * mc) per = ((per + mc - 1) / mc) * mc;
+    h->first = std::min(d, rank * per);
+    h->dl = std::max(0, std::min(per, d - h->first));
+    h->chunk_base = h->first % mc;
+    h->nchunks = std::max(1, (per + mc - 1) / mc + ((per % mc) && world > 1 ? 1 : 0));
+    h->per_mode = (flags & TK_FLAG_REFERENCE_H1) ? 0 : 1;
+    h->ncls = h->per_mode ? std::max(h->dl, 1) : 1;
+
+    TK_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    const size_t dl = std::max(h->dl, 1);
+    TK_TRY(h->V.alloc(dl * (size_t)h->ncol * h->ldv));
+    TK_TRY(h->b.alloc(dl * (size_t)h->ldv));
+    TK_TRY(h->T.alloc(dl * 3 * (size_t)h->ncol));
+    if (variant == TK_ARNOLDI) TK_TRY(h->Hd.alloc(dl * (size_t)h->ncol * h->ncol));
+    TK_TRY(h->bt.alloc(dl * (size_t)h->ncol));
+    TK_TRY(h->g.alloc(dl * (size_t)h->ncol));
+    TK_TRY(h->S.alloc(dl));
+    TK_TRY(h->orthS.alloc(h->ncol));
+    TK_TRY(h->bnorm2.alloc(dl));
+    TK_TRY(h->fallbacks.alloc(dl));
+    TK_TRY(h->mode_op_d.alloc(dl));
+    TK_TRY(h->status_d.alloc(1));
+    TK_TRY(h->term_k_d.alloc(1));
+    TK_TRY(h->eigfail_d.alloc(1));
+    TK_TRY(h->niter_d.alloc(1));
+    TK_TRY(h->bnorm_d.alloc(1));
+    TK_TRY(h->relres_d.alloc(nmax));
+    TK_TRY(h->projres_d.alloc(nmax));
+    TK_TRY(h->orth_d.alloc(nmax));
+    TK_TRY(h->detail_d.alloc((size_t)(nmax + 1) * 8));
+    TK_TRY(h->Tq.alloc(3 * (size_t)h->ncol));
+    h->mode_op.assign(dl, -1);
+    h->rhs_set.assign(dl, 0);
+    h->sched.assign(nmax + 1, SchedEntry());
+    TK_CUDA(cudaMallocHost(&h->status_ring, 8 * sizeof(int)));
+    h->ring_ev.resize(8);
+    for (auto& e : h->ring_ev) TK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (world > 1) {
+        TK_TRY(nccl_bind());
+        ncclUniqueId id;
+        std::memcpy(&id, unique_id, 128);
+        TK_NCCL(g_nccl.CommInitRank(&h->comm, world, id, rank));
+    }
+    *out = h.release();
+    return 0;
+}
+
+void tk_destroy(tk_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (auto e : h->ev_pool) cudaEventDestroy(e);
+    for (auto e : h->ring_ev) cudaEventDestroy(e);
+    if (h->status_ring) cudaFreeHost(h->status_ring);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int tk_local_modes(const tk_handle* h, int32_t* first, int32_t* count) {
+    if (!h) return set_error(TK_EINVAL, "null handle");
+    if (first) *first = h->first;
+    if (count) *count = h->dl;
+    return 0;
+}
+
+int tk_set_operator_csc(tk_handle* h, int32_t s, int64_t n, const int64_t* colptr, const int64_t* rowval, const double* nzval) {
+    bool local = false;
+    TK_TRY(check_mode(h, s, &local));
+    if (n != h->n) return set_error(TK_EINVAL, "operator order %lld != n = %d (system.jl:27-28)", (long long)n, h->n);
+    if (!colptr || !rowval || !nzval) return set_error(TK_EINVAL, "null CSC array");
+    if (!local) return 0;
+    TK_CUDA(cudaSetDevice(h->device));
+    if (colptr[0] != 1) return set_error(TK_EINVAL, "colptr must be 1-based (Julia SparseMatrixCSC)");
+    const int64_t nnz = colptr[n] - 1;
+    std::set<long long> offs;
+    for (int64_t j = 0; j < n; ++j) {
+        if (colptr[j + 1] < colptr[j]) return set_error(TK_EINVAL, "colptr not monotone");
+        for (int64_t p = colptr[j] - 1; p < colptr[j + 1] - 1; ++p) {
+            const int64_t i = rowval[p] - 1;
+            if (i < 0 || i >= n) return set_error(TK_EINVAL, "rowval out of range");
+            if (offs.size() <= (size_t)MAX_DIAG) offs.insert(j - i);
+        }
+    }
+    std::unique_ptr<HostOp> op(new HostOp());
+    op->ld = n; op->nnz = nnz;
+    if (offs.size() <= (size_t)MAX_DIAG && !offs.empty()) {
+        op->type = OP_DIA;
+        op->ndiag = (int)offs.size();
+        std::map<long long, int> idx;
+        int c = 0;
+        for (long long o : offs) { op->offs[c] = (int)o; idx[o] = c++; }
+        std::vector<double> diag((size_t)op->ndiag * n, 0.0);
+        for (int64_t j = 0; j < n; ++j)
+            for (int64_t p = colptr[j] - 1; p < colptr[j + 1] - 1; ++p) {
+                const int64_t i = rowval[p] - 1;
+                diag[(size_t)idx[j - i] * n + i] += nzval[p];
+            }
+        TK_TRY(op->vals.alloc(diag.size(), false));
+        TK_CUDA(cudaMemcpy(op->vals.p, diag.data(), 8 * diag.size(), cudaMemcpyHostToDevice));
+    } else {
+        op->type = OP_CSR;
+        std::vector<int> rowptr(n + 1, 0);
+        for (int64_t p = 0; p < nnz; ++p) rowptr[rowval[p]]++;   // rowval is 1-based: counts land at row+1
+        for (int64_t i = 0; i < n; ++i) rowptr[i + 1] += rowptr[i];
+        std::vector<int> fill(rowptr.begin(), rowptr.end() - 1), colidx(std::max<int64_t>(nnz, 1));
+        std::vector<double> val(std::max<int64_t>(nnz, 1));
+        for (int64_t j = 0; j < n; ++j)
+            for (int64_t p = colptr[j] - 1; p < colptr[j + 1] - 1; ++p) {
+                const int64_t i = rowval[p] - 1;
+                const int q = fill[i]++;
+                colidx[q] = (int)j;
+                val[q] = nzval[p];
+            }
+        TK_TRY(op->vals.alloc(val.size(), false));
+        TK_TRY(op->rowptr.alloc(rowptr.size(), false));
+        TK_TRY(op->colidx.alloc(colidx.size(), false));
+        TK_CUDA(cudaMemcpy(op->vals.p, val.data(), 8 * val.size(), cudaMemcpyHostToDevice));
+        TK_CUDA(cudaMemcpy(op->rowptr.p, rowptr.data(), 4 * rowptr.size(), cudaMemcpyHostToDevice));
+        TK_CUDA(cudaMemcpy(op->colidx.p, colidx.data(), 4 * colidx.size(), cudaMemcpyHostToDevice));
+    }
+    h->ops.push_back(std::move(op));
+    h->mode_op[s - h->first] = (int)h->ops.size() - 1;
+    h->ops_dirty = true;
+    return 0;
+}
+
+int tk_set_operator_dense(tk_handle* h, int32_t s, int64_t n, const double* a, char uplo) {
+    bool local = false;
+    TK_TRY(check_mode(h, s, &local));
+    if (n != h->n) return set_error(TK_EINVAL, "operator order %lld != n = %d", (long long)n, h->n);
+    if (!a) return set_error(TK_EINVAL, "null matrix");
+    if (uplo != 'L' && uplo != 'F') return set_error(TK_EINVAL, "uplo must be 'L' or 'F'");
+    if (!local) return 0;
+    TK_CUDA(cudaSetDevice(h->device));
+    std::unique_ptr<HostOp> op(new HostOp());
+    op->type = OP_DENSE; op->ld = n; op->nnz = n * n;
+    TK_TRY(op->vals.alloc((size_t)n * n, false));
+    if (uplo == 'F') {
+        TK_CUDA(cudaMemcpy(op->vals.p, a, 8 * (size_t)n * n, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<double> full((size_t)n * n);
+        for (int64_t j = 0; j < n; ++j)
+            for (int64_t i = j; i < n; ++i) {
+                full[(size_t)j * n + i] = a[(size_t)j * n + i];
+                full[(size_t)i * n + j] = a[(size_t)j * n + i];
+            }
+        TK_CUDA(cudaMemcpy(op->vals.p, full.data(), 8 * full.size(), cudaMemcpyHostToDevice));
+    }
+    h->ops.push_back(std::move(op));
+    h->mode_op[s - h->first] = (int)h->ops.size() - 1;
+    h->ops_dirty = true;
+    return 0;
+}
+
+int tk_share_operator(tk_handle* h, int32_t s_dst, int32_t s_src) {
+    bool ld = false, ls = false;
+    TK_TRY(check_mode(h, s_dst, &ld));
+    TK_TRY(check_mode(h, s_src, &ls));
+    if (!ld) return 0;
+    if (!ls) return set_error(TK_EINVAL, "mode %d is owned by another rank; set its operator on this rank first", s_src);
+    if (h->mode_op[s_src - h->first] < 0) return set_error(TK_ESTATE, "operator of mode %d not set", s_src);
+    h->mode_op[s_dst - h->first] = h->mode_op[s_src - h->first];
+    h->ops_dirty = true;
+    return 0;
+}
+
+int tk_set_rhs(tk_handle* h, int32_t s, const double* b, int64_t n) {
+    bool local = false;
+    TK_TRY(check_mode(h, s, &local));
+    if (n != h->n) return set_error(TK_EINVAL, "rhs length %lld != n = %d (system.jl:28)", (long long)n, h->n);
+    if (!b) return set_error(TK_EINVAL, "null rhs");
+    if (!local) return 0;
+    TK_CUDA(cudaSetDevice(h->device));
+    TK_CUDA(cudaMemcpyAsync(h->b.p + (size_t)(s - h->first) * h->ldv, b, 8 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    h->rhs_set[s - h->first] = 1;
+    return 0;
+}
+
+int tk_set_rhs_all(tk_handle* h, const double* b, int64_t n) {
+    if (!h || !b) return set_error(TK_EINVAL, "null argument");
+    if (n != h->n) return set_error(TK_EINVAL, "rhs length %lld != n = %d", (long long)n, h->n);
+    TK_CUDA(cudaSetDevice(h->device));
+    for (int s = 0; s < h->dl; ++s)
+        TK_CUDA(cudaMemcpyAsync(h->b.p + (size_t)s * h->ldv, b, 8 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    std::fill(h->rhs_set.begin(), h->rhs_set.end(), 1);
+    return 0;
+}
+
+int tk_set_schedule(tk_handle* h, int32_t k, double lambda_min, int32_t t, const double* alpha, const double* omega) {
+    if (!h || !alpha || !omega) return set_error(TK_EINVAL, "null argument");
+    if (k < 2 || k > h->nmax) return set_error(TK_EINVAL, "k = %d outside 2..nmax", k);
+    if (t < 1 || t > 4096) return set_error(TK_EINVAL, "bad term count t = %d", t);
+    if (!(lambda_min > 0.0)) return set_error(TK_EINVAL, "lambda_min must be positive");
+    SchedEntry& se = h->sched[k];
+    if (!se.set || se.t != t) {
+        se.off = h->alpha_pool.size();
+        h->alpha_pool.resize(se.off + t);
+        h->omega_pool.resize(se.off + t);
+    }
+    std::memcpy(h->alpha_pool.data() + se.off, alpha, 8 * (size_t)t);
+    std::memcpy(h->omega_pool.data() + se.off, omega, 8 * (size_t)t);
+    se.set = true; se.lambda_min = lambda_min; se.t = t;
+    h->sched_dirty = true;
+    return 0;
+}
+
+int tk_schedule_laplace(tk_handle* h, double tol) {
+    if (!h) return set_error(TK_EINVAL, "null handle");
+    for (int k = 2; k <= h->nmax; ++k) {
+        double lmin, lmax;
+        laplace_extremes(h->d, h->n, k, &lmin, &lmax);
+        const double kappa = lmax * (1.0 / lmin);   // eigenvalues.jl:360
+        int t, dg, od;
+        const double *om, *al;
+        TK_TRY(tables_sym_lookup(kappa, tol, &t, &dg, &od, &om, &al));
+        TK_TRY(tk_set_schedule(h, k, lmin, t, al, om));
+    }
+    return 0;
+}
+
+int tk_begin(tk_handle* h) {
+    if (!h) return set_error(TK_EINVAL, "null handle");
+    TK_CUDA(cudaSetDevice(h->device));
+    TK_TRY(begin_solve(h));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int tk_step_bases(tk_handle* h, int32_t k) {
+    if (!h || !h->begun) return set_error(TK_ESTATE, "call tk_begin first");
+    if (k < 2 || k > h->nmax) return set_error(TK_EINVAL, "k = %d outside 2..nmax", k);
+    TK_CUDA(cudaSetDevice(h->device));
+    TK_TRY(enqueue_step_bases(h, k));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int tk_compress(tk_handle* h, int32_t k) {
+    if (!h || !h->begun) return set_error(TK_ESTATE, "call tk_begin first");
+    if (k < 2 || k > h->nmax) return set_error(TK_EINVAL, "k = %d outside 2..nmax", k);
+    TK_CUDA(cudaSetDevice(h->device));
+    TK_TRY(upload_schedule(h));
+    TK_TRY(alloc_work(h));
+    TK_TRY(enqueue_compress(h, k));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int tk_residual(tk_handle* h, int32_t k, double tol, double* out8) {
+    if (!h || !h->begun || h->last_k != k) return set_error(TK_ESTATE, "call tk_compress(k) first");
+    TK_CUDA(cudaSetDevice(h->device));
+    TK_TRY(enqueue_residual(h, k, tol));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    if (out8) TK_CUDA(cudaMemcpy(out8, h->detail_d.p + (size_t)k * 8, 64, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int tk_solve(tk_handle* h, double tol, int32_t* status, int64_t* niter, int32_t* term_k, double* relres, double* projres,
+             double* orth) {
+    if (!h) return set_error(TK_EINVAL, "null handle");
+    TK_CUDA(cudaSetDevice(h->device));
+    TK_TRY(upload_schedule(h));
+    TK_TRY(alloc_work(h));
+    TK_TRY(begin_solve(h));
+    const int LAG = 3, RING = 8;
+    int st = ST_RUNNING;
+    for (int k = 2; k <= h->nmax; ++k) {
+        if (k - LAG >= 2) {
+            const int slot = (k - LAG) % RING;
+            TK_CUDA(cudaEventSynchronize(h->ring_ev[slot]));
+            if (h->status_ring[slot] != ST_RUNNING) break;
+        }
+        TK_TRY(enqueue_step_bases(h, k));
+        TK_TRY(enqueue_compress(h, k));
+        TK_TRY(enqueue_residual(h, k, tol));
+        const int slot = k % RING;
+        TK_CUDA(cudaMemcpyAsync(&h->status_ring[slot], h->status_d.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        TK_CUDA(cudaEventRecord(h->ring_ev[slot], h->stream));
+    }
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    int tk_ = 0, eigfail = 0;
+    long long nit = 0;
+    TK_CUDA(cudaMemcpy(&st, h->status_d.p, sizeof(int), cudaMemcpyDeviceToHost));
+    TK_CUDA(cudaMemcpy(&tk_, h->term_k_d.p, sizeof(int), cudaMemcpyDeviceToHost));
+    TK_CUDA(cudaMemcpy(&nit, h->niter_d.p, sizeof(long long), cudaMemcpyDeviceToHost));
+    TK_CUDA(cudaMemcpy(&eigfail, h->eigfail_d.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (h->nmax < 2) { st = ST_NMAX; tk_ = 1; }
+    if (relres) TK_CUDA(cudaMemcpy(relres, h->relres_d.p, 8 * (size_t)h->nmax, cudaMemcpyDeviceToHost));
+    if (projres) TK_CUDA(cudaMemcpy(projres, h->projres_d.p, 8 * (size_t)h->nmax, cudaMemcpyDeviceToHost));
+    if (orth) TK_CUDA(cudaMemcpy(orth, h->orth_d.p, 8 * (size_t)h->nmax, cudaMemcpyDeviceToHost));
+    TK_TRY(collect_timing(h));
+    if (status) *status = st;
+    if (niter) *niter = nit;
+    if (term_k) *term_k = tk_;
+    if (eigfail) return set_error(TK_ESTATE, "tridiagonal eigensolver did not converge");
+    if (st == ST_RUNNING) return set_error(TK_ESTATE, "solve left the loop while still running");
+    return 0;
+}
+
+int tk_solution_rank(tk_handle* h, int32_t* t) {
+    if (!h || !t) return set_error(TK_EINVAL, "null argument");
+    *t = h->last_t;
+    return 0;
+}
+
+int tk_get_solution(tk_handle* h, int32_t s, double* lambda, double* fmat, int32_t force) {
+    bool local = false;
+    TK_TRY(check_mode(h, s, &local));
+    if (h->last_k < 2) return set_error(TK_ESTATE, "no compressed solution available");
+    TK_CUDA(cudaSetDevice(h->device));
+    int st = ST_RUNNING;
+    TK_CUDA(cudaMemcpy(&st, h->status_d.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st != ST_CONVERGED && !force) return set_error(TK_ESTATE, "solve did not converge (status %d); pass force to read the last iterate", st);
+    int k = h->last_k;
+    if (st != ST_RUNNING) {
+        int tk_ = 0;
+        TK_CUDA(cudaMemcpy(&tk_, h->term_k_d.p, sizeof(int), cudaMemcpyDeviceToHost));
+        if (tk_ >= 2) k = std::min(k, tk_);
+    }
+    const SchedEntry& se = h->sched[k];
+    const int t = se.t, tld = (t + 3) & ~3;
+    if (lambda) {
+        const double lam_inv = 1.0 / se.lambda_min;
+        for (int j = 0; j < t; ++j) lambda[j] = lam_inv * h->omega_pool[se.off + j];   // y.lambda, tensor_krylov_method.jl:23
+    }
+    if (!local || !fmat) return 0;
+    const int sl = s - h->first;
+    DevBuf<double> X;
+    TK_TRY(X.alloc((size_t)h->n * t, false));
+    dim3 grid((h->n + 255) / 256, (t + BM_TJ - 1) / BM_TJ);
+    const size_t smem = (size_t)k * BM_TJ * 8;
+    basis_mul_kernel<<<grid, 256, smem, h->stream>>>(h->V.p + (size_t)sl * h->ncol * h->ldv, h->ldv, h->n, k,
+                                                     h->Y.p + (size_t)sl * h->ystride, tld, t, X.p);
+    TK_CUDA(cudaGetLastError());
+    TK_CUDA(cudaMemcpyAsync(fmat, X.p, 8 * (size_t)h->n * t, cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int tk_get_H(tk_handle* h, int32_t s, double* H) {
+    bool local = false;
+    TK_TRY(check_mode(h, s, &local));
+    if (!H) return set_error(TK_EINVAL, "null output");
+    if (!local) return set_error(TK_EINVAL, "mode %d is owned by another rank", s);
+    TK_CUDA(cudaSetDevice(h->device));
+    const int nc = h->ncol, sl = s - h->first;
+    if (h->Hd.p) {
+        TK_CUDA(cudaMemcpy(H, h->Hd.p + (size_t)sl * nc * nc, 8 * (size_t)nc * nc, cudaMemcpyDeviceToHost));
+        return 0;
+    }
+    std::vector<double> T(3 * (size_t)nc);
+    TK_CUDA(cudaMemcpy(T.data(), h->T.p + (size_t)sl * 3 * nc, 8 * T.size(), cudaMemcpyDeviceToHost));
+    std::fill(H, H + (size_t)nc * nc, 0.0);
+    for (int j = 0; j < nc; ++j) {
+        H[(size_t)j * nc + j] = T[j];
+        if (j + 1 < nc) {
+            H[(size_t)j * nc + (j + 1)] = T[nc + j];         // H[j+2, j+1] (1-based): sub-diagonal
+            H[(size_t)(j + 1) * nc + j] = T[2 * nc + j];     // H[j+1, j+2]: super-diagonal
+        }
+    }
+    return 0;
+}
+
+int tk_get_V(tk_handle* h, int32_t s, int32_t col, double* v) {
+    bool local = false;
+    TK_TRY(check_mode(h, s, &local));
+    if (!v || col < 1 || col > h->ncol) return set_error(TK_EINVAL, "bad column %d", col);
+    if (!local) return set_error(TK_EINVAL, "mode %d is owned by another rank", s);
+    TK_CUDA(cudaSetDevice(h->device));
+    TK_CUDA(cudaMemcpy(v, h->V.p + ((size_t)(s - h->first) * h->ncol + (col - 1)) * h->ldv, 8 * (size_t)h->n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int tk_get_bt(tk_handle* h, int32_t s, double* bt) {
+    bool local = false;
+    TK_TRY(check_mode(h, s, &local));
+    if (!bt) return set_error(TK_EINVAL, "null output");
+    if (!local) return set_error(TK_EINVAL, "mode %d is owned by another rank", s);
+    TK_CUDA(cudaSetDevice(h->device));
+    TK_CUDA(cudaMemcpy(bt, h->bt.p + (size_t)(s - h->first) * h->ncol, 8 * (size_t)h->ncol, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int tk_get_Y(tk_handle* h, int32_t s, int32_t k, double* Y, int32_t* t) {
+    bool local = false;
+    TK_TRY(check_mode(h, s, &local));
+    if (h->last_k != k) return set_error(TK_ESTATE, "Y of iteration %d is not resident (last compress was k=%d)", k, h->last_k);
+    if (!local) return set_error(TK_EINVAL, "mode %d is owned by another rank", s);
+    TK_CUDA(cudaSetDevice(h->device));
+    const int tt = h->last_t, tld = h->last_tld;
+    if (t) *t = tt;
+    if (!Y) return 0;
+    std::vector<double> rm((size_t)k * tld);
+    TK_CUDA(cudaMemcpy(rm.data(), h->Y.p + (size_t)(s - h->first) * h->ystride, 8 * rm.size(), cudaMemcpyDeviceToHost));
+    for (int j = 0; j < tt; ++j)
+        for (int r = 0; r < k; ++r) Y[(size_t)j * k + r] = rm[(size_t)r * tld + j];
+    return 0;
+}
+
+int tk_get_eig(tk_handle* h, int32_t s, int32_t k, double* theta, double* Q) {
+    bool local = false;
+    TK_TRY(check_mode(h, s, &local));
+    if (h->last_k != k) return set_error(TK_ESTATE, "eigendecomposition of iteration %d is not resident", k);
+    if (!local) return set_error(TK_EINVAL, "mode %d is owned by another rank", s);
+    TK_CUDA(cudaSetDevice(h->device));
+    const int cls = h->per_mode ? s - h->first : 0;
+    if (theta) TK_CUDA(cudaMemcpy(theta, h->theta.p + (size_t)cls * h->ncol, 8 * (size_t)k, cudaMemcpyDeviceToHost));
+    if (Q) {
+        std::vector<double> q((size_t)h->ldq * k);
+        TK_CUDA(cudaMemcpy(q.data(), h->Q.p + (size_t)cls * h->ldq * h->ldq, 8 * q.size(), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < k; ++i)
+            for (int r = 0; r < k; ++r) Q[(size_t)i * k + r] = q[(size_t)i * h->ldq + r];
+    }
+    return 0;
+}
+
+int tk_get_orth_state(tk_handle* h, int32_t s, double* S, int32_t* fallbacks) {
+    bool local = false;
+    TK_TRY(check_mode(h, s, &local));
+    if (!local) return set_error(TK_EINVAL, "mode %d is owned by another rank", s);
+    TK_CUDA(cudaSetDevice(h->device));
+    if (S) TK_CUDA(cudaMemcpy(S, h->S.p + (s - h->first), 8, cudaMemcpyDeviceToHost));
+    if (fallbacks) TK_CUDA(cudaMemcpy(fallbacks, h->fallbacks.p + (s - h->first), 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int tk_tridiag_eig_batched(int32_t device, int32_t nb, int32_t k, const double* diag, const double* sub, double* theta, double* Q) {
+    if (nb < 1 || k < 1 || !diag || !theta || (k > 1 && !sub)) return set_error(TK_EINVAL, "bad arguments");
+    TK_CUDA(cudaSetDevice(device));
+    const int ncol = k;
+    std::vector<double> T((size_t)nb * 2 * ncol, 0.0);
+    for (int p = 0; p < nb; ++p) {
+        std::memcpy(&T[(size_t)p * 2 * ncol], diag + (size_t)p * k, 8 * (size_t)k);
+        if (k > 1) std::memcpy(&T[(size_t)p * 2 * ncol + ncol], sub + (size_t)p * (k - 1), 8 * (size_t)(k - 1));
+    }
+    DevBuf<double> Td, thd, Qd;
+    DevBuf<int> fail;
+    TK_TRY(Td.alloc(T.size(), false));
+    TK_TRY(thd.alloc((size_t)nb * k));
+    TK_TRY(Qd.alloc((size_t)nb * k * k));
+    TK_TRY(fail.alloc(1));
+    TK_CUDA(cudaMemcpy(Td.p, T.data(), 8 * T.size(), cudaMemcpyHostToDevice));
+    TK_TRY(launch_eig(Td.p, 2LL * ncol, ncol, k, nb, thd.p, k, Qd.p, (long long)k * k, k, nullptr, fail.p, 0));
+    TK_CUDA(cudaDeviceSynchronize());
+    int f = 0;
+    TK_CUDA(cudaMemcpy(&f, fail.p, 4, cudaMemcpyDeviceToHost));
+    TK_CUDA(cudaMemcpy(theta, thd.p, 8 * (size_t)nb * k, cudaMemcpyDeviceToHost));
+    if (Q) TK_CUDA(cudaMemcpy(Q, Qd.p, 8 * (size_t)nb * k * k, cudaMemcpyDeviceToHost));
+    if (f) return set_error(TK_ESTATE, "tridiagonal eigensolver did not converge");
+    return 0;
+}
+
+int tk_get_timing(tk_handle* h, int32_t which, double* ms_total, int64_t* launches, double* algorithmic_bytes) {
+    if (!h || which < 0 || which >= TM_KINDS) return set_error(TK_EINVAL, "bad timing kind %d", which);
+    if (ms_total) *ms_total = h->tm_ms[which];
+    if (launches) *launches = h->tm_launches[which];
+    if (algorithmic_bytes) *algorithmic_bytes = h->tm_bytes[which];
+    return 0;
+}
+
+int tk_launch_count(tk_handle* h, int64_t* launches) {
+    if (!h || !launches) return set_error(TK_EINVAL, "null argument");
+    *launches = h->launches;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,286 @@
+// tk_krylov.cuh -- kernel family (1): one launch advances the Krylov basis of every mode.
+//
+//   init_basis_kernel     V[:,1] = b/||b||, b~[1]                (decompositions.jl:112-118, utils.jl:456-464)
+//   lanczos_ttr_kernel    3-term recurrence step                (orthogonal_bases.jl:39-67)
+//   gram_row_kernel       g_j = v_j . v_{k+1}, j = 1..k+1       (the only NEW row of V'V; orthogonal_bases.jl:119,250-257)
+//   monitor_kernel        loss test + MGS fallback              (orthogonal_bases.jl:119-131)
+//   arnoldi_mgs_kernel    two-pass modified Gram-Schmidt step   (orthogonal_bases.jl:15-37)
+#pragma once
+#include "tk_device.cuh"
+
+namespace tk {
+
+// ------------------------------------------------------------------------------------------
+// k = 0: normalise b into the first basis vector and start b~.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) init_basis_kernel(KrylovParams p, double* bnorm2) {
+    __shared__ double scratch[32];
+    const int s = blockIdx.x, n = p.n;
+    const double* b = p.b + (long long)s * p.ldv;
+    double* v1 = p.V + (long long)s * p.vstride;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc = fma(b[i], b[i], acc);
+    const double bb = block_sum(acc, scratch);
+    const double inv = 1.0 / sqrt(bb);                 // inv(norm(b)) .* b
+    acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double x = inv * b[i];
+        v1[i] = x;
+        acc = fma(x, b[i], acc);
+    }
+    const double bt0 = block_sum(acc, scratch);
+    if (threadIdx.x == 0) {
+        p.bt[(long long)s * p.ncol] = bt0;             // b~_s[1] = v_1 . b_s
+        bnorm2[s] = bb;                                // for kronprodnorm(b), tensor_struct.jl:271-281
+        p.S[s] = 0.0;
+        p.fallbacks[s] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// 3-term Lanczos step k for every mode.  CPM CTAs (one thread-block cluster) share a mode and
+// split the rows; the three reductions go through distributed shared memory.
+//   u = A v_k - beta_{k-1} v_{k-1};  H[k,k] = u.v_k;  v^ = u - H[k,k] v_k;  beta = ||v^||
+//   v_{k+1} = v^ / beta (zeros if beta == 0);  H[k+1,k] = H[k,k+1] = beta;  b~[k+1] = v_{k+1}.b
+// Algorithmic HBM bytes per mode: (ndiag + 4) * 8 * n  (diagonals, v_k, v_{k-1}, b read; v_{k+1} written).
+// ------------------------------------------------------------------------------------------
+template <int CPM>
+__device__ __forceinline__ double cluster_sum(double blockval, double* slot) {
+    if (CPM == 1) return blockval;
+    cg::cluster_group cl = cg::this_cluster();
+    if (threadIdx.x == 0) *slot = blockval;
+    cl.sync();
+    double tot = 0.0;
+#pragma unroll
+    for (int r = 0; r < CPM; ++r) tot += *cl.map_shared_rank(slot, r);
+    return tot;
+}
+
+template <int CPM>
+__global__ void __launch_bounds__(512) lanczos_ttr_kernel(KrylovParams p, int k) {
+    if (*p.status != ST_RUNNING) return;
+    extern __shared__ double smem[];
+    __shared__ double scratch[32];
+    __shared__ double slots[4];
+    const int s = blockIdx.x / CPM, part = blockIdx.x % CPM, n = p.n;
+    const int chunk = (((n + CPM - 1) / CPM) + 1) & ~1;
+    const int lo = part * chunk, hi = min(n, lo + chunk);
+    double* u = smem;  // rows [lo, hi)
+    const OpDesc& op = p.ops[p.mode_op[s]];
+    double* Vs = p.V + (long long)s * p.vstride;
+    const double* vk = Vs + (long long)(k - 1) * p.ldv;
+    const double* vkm1 = (k >= 2) ? Vs + (long long)(k - 2) * p.ldv : nullptr;
+    double* vnew = Vs + (long long)k * p.ldv;
+    double* T = p.T + (long long)s * 3 * p.ncol;
+    const double beta_prev = (k >= 2) ? T[2 * p.ncol + (k - 2)] : 0.0;  // H[k-1,k]  (decompositions.jl:78)
+
+    double acc = 0.0;
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        double ui = apply_row(op, vk, i, n);
+        if (vkm1) ui -= beta_prev * vkm1[i];
+        u[i - lo] = ui;
+        acc = fma(ui, vk[i], acc);
+    }
+    const double alpha = cluster_sum<CPM>(block_sum(acc, scratch), &slots[0]);
+
+    acc = 0.0;
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const double w = u[i - lo] - alpha * vk[i];
+        u[i - lo] = w;
+        acc = fma(w, w, acc);
+    }
+    const double beta = sqrt(cluster_sum<CPM>(block_sum(acc, scratch), &slots[1]));
+
+    const double inv = (beta == 0.0) ? 0.0 : 1.0 / beta;
+    const double* b = p.b + (long long)s * p.ldv;
+    acc = 0.0;
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const double x = inv * u[i - lo];
+        vnew[i] = x;
+        acc = fma(x, b[i], acc);
+    }
+    const double btn = cluster_sum<CPM>(block_sum(acc, scratch), &slots[2]);
+    if (part == 0 && threadIdx.x == 0) {
+        T[k - 1] = alpha;                   // H[k,k]
+        T[p.ncol + (k - 1)] = beta;         // H[k+1,k]
+        T[2 * p.ncol + (k - 1)] = beta;     // H[k,k+1]   update_subdiagonals!, decompositions.jl:180-186
+        p.bt[(long long)s * p.ncol + k] = btn;
+    }
+    if (CPM > 1) cg::this_cluster().sync();  // keep every CTA's slots alive until all peers have read them
+}
+
+// ------------------------------------------------------------------------------------------
+// Orthogonality monitor: the newest row of the Gram matrix V'V.
+//   g[s][j] = V_s[:,j] . V_s[:,ncols-1],  j = 0..ncols-1
+// The reference forms the whole (k+1)x(k+1) Gram matrix with dgemm at every step in every mode
+// (orthogonal_bases.jl:119); only this row is new, the rest is carried in S[s].
+// grid = (column chunks, modes); a warp streams one column (16-byte loads, 8 in flight per lane)
+// against the new vector staged in shared memory.  HBM-bound: 8*n bytes per column.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gram_row_kernel(KrylovParams p, int ncols, int cols_per_cta, int mode_base,
+                                                       int w_in_smem) {
+    if (*p.status != ST_RUNNING) return;
+    extern __shared__ double smem[];
+    const int s = mode_base + blockIdx.y, n = p.n;
+    const int c0 = blockIdx.x * cols_per_cta, c1 = min(ncols, c0 + cols_per_cta);
+    const double* Vs = p.V + (long long)s * p.vstride;
+    const double* wg = Vs + (long long)(ncols - 1) * p.ldv;
+    const int nq = n >> 1;
+    if (w_in_smem) {
+        const double2* w2 = reinterpret_cast<const double2*>(wg);
+        double2* s2 = reinterpret_cast<double2*>(smem);
+        for (int q = threadIdx.x; q < nq; q += blockDim.x) s2[q] = w2[q];
+        if ((n & 1) && threadIdx.x == 0) smem[n - 1] = wg[n - 1];
+        __syncthreads();
+    }
+    const double* w = w_in_smem ? smem : wg;
+    const double2* w2 = reinterpret_cast<const double2*>(w);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    double* g = p.g + (long long)s * p.ncol;
+    for (int j = c0 + warp; j < c1; j += nwarp) {
+        const double* col = Vs + (long long)j * p.ldv;
+        const double2* c2 = reinterpret_cast<const double2*>(col);
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0;
+        int q = lane;
+        for (; q + 224 < nq; q += 256) {
+            const double2 x0 = ld_stream2(c2 + q), x1 = ld_stream2(c2 + q + 32), x2 = ld_stream2(c2 + q + 64),
+                          x3 = ld_stream2(c2 + q + 96), x4 = ld_stream2(c2 + q + 128), x5 = ld_stream2(c2 + q + 160),
+                          x6 = ld_stream2(c2 + q + 192), x7 = ld_stream2(c2 + q + 224);
+            const double2 y0 = w2[q], y1 = w2[q + 32], y2 = w2[q + 64], y3 = w2[q + 96], y4 = w2[q + 128],
+                          y5 = w2[q + 160], y6 = w2[q + 192], y7 = w2[q + 224];
+            a0 = fma(x0.x, y0.x, a0); a0 = fma(x0.y, y0.y, a0);
+            a1 = fma(x1.x, y1.x, a1); a1 = fma(x1.y, y1.y, a1);
+            a2 = fma(x2.x, y2.x, a2); a2 = fma(x2.y, y2.y, a2);
+            a3 = fma(x3.x, y3.x, a3); a3 = fma(x3.y, y3.y, a3);
+            a4 = fma(x4.x, y4.x, a4); a4 = fma(x4.y, y4.y, a4);
+            a5 = fma(x5.x, y5.x, a5); a5 = fma(x5.y, y5.y, a5);
+            a6 = fma(x6.x, y6.x, a6); a6 = fma(x6.y, y6.y, a6);
+            a7 = fma(x7.x, y7.x, a7); a7 = fma(x7.y, y7.y, a7);
+        }
+        for (; q < nq; q += 32) {
+            const double2 x0 = ld_stream2(c2 + q);
+            const double2 y0 = w2[q];
+            a0 = fma(x0.x, y0.x, a0); a0 = fma(x0.y, y0.y, a0);
+        }
+        if ((n & 1) && lane == 0) a0 = fma(col[n - 1], w[n - 1], a0);
+        double acc = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+        acc = warp_sum(acc);
+        if (lane == 0) g[j] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// CTA-wide modified Gram-Schmidt step k (orthogonal_bases.jl:15-37) for mode s.
+// v: working vector of n doubles (shared or global scratch); every thread owns the rows
+// i = tid, tid + blockDim, ... so the dot/axpy sequence needs no barrier besides the reduction.
+// hcol[0..k-1] = H[1:k,k], hcol[k] = H[k+1,k].  Writes V[:,k+1] and b~[k+1].
+// ------------------------------------------------------------------------------------------
+__device__ void mgs_step_cta(const KrylovParams& p, int s, int k, double* v, double* hcol, double* scratch) {
+    const int n = p.n;
+    const OpDesc& op = p.ops[p.mode_op[s]];
+    double* Vs = p.V + (long long)s * p.vstride;
+    const double* vk = Vs + (long long)(k - 1) * p.ldv;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v[i] = apply_row(op, vk, i, n);
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int c = 0; c < k; ++c) {
+            const double* col = Vs + (long long)c * p.ldv;
+            double acc = 0.0;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) acc = fma(v[i], col[i], acc);
+            const double h = block_sum(acc, scratch);
+            if (threadIdx.x == 0) hcol[c] = pass ? hcol[c] + h : h;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) v[i] = fma(-h, col[i], v[i]);
+        }
+    }
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc = fma(v[i], v[i], acc);
+    const double beta = sqrt(block_sum(acc, scratch));
+    const double inv = 1.0 / beta;  // no zero-norm guard in the reference (:35-36)
+    double* vnew = Vs + (long long)k * p.ldv;
+    const double* b = p.b + (long long)s * p.ldv;
+    acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double x = v[i] * inv;
+        vnew[i] = x;
+        v[i] = x;
+        acc = fma(x, b[i], acc);
+    }
+    const double btn = block_sum(acc, scratch);
+    if (threadIdx.x == 0) {
+        hcol[k] = beta;
+        p.bt[(long long)s * p.ncol + k] = btn;
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// After gram_row_kernel: fold the new Gram row into S = ||V'V - I||_F^2 and, for
+// TensorLanczosReorth, run the MGS fallback when sqrt(S) > sqrt(eps) (orthogonal_bases.jl:119-131).
+// newcol = 0-based index of the newest column (= k for step k).  One CTA per listed mode;
+// CTAs whose mode does not fall back leave after a k-term sum.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) monitor_kernel(KrylovParams p, int newcol, int mode_base, int reorth,
+                                                      double* vscratch /* [modes][ldv] or nullptr -> shared */) {
+    if (*p.status != ST_RUNNING) return;
+    extern __shared__ double smem[];
+    __shared__ double scratch[32];
+    const int s = mode_base + blockIdx.x, n = p.n, k = newcol;  // k = reference step index
+    double* g = p.g + (long long)s * p.ncol;
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < newcol; j += blockDim.x) acc = fma(g[j], g[j], acc);
+    double off2 = block_sum(acc, scratch);
+    double dd = g[newcol] - 1.0;
+    double Snew = p.S[s] + 2.0 * off2 + dd * dd;
+    if (reorth && sqrt(Snew) > SQRT_EPS) {
+        double* hcol = smem;                                   // ncol doubles
+        double* v = vscratch ? vscratch + (long long)s * p.ldv : smem + p.ncol;
+        mgs_step_cta(p, s, k, v, hcol, scratch);
+        double* T = p.T + (long long)s * 3 * p.ncol;
+        if (threadIdx.x == 0) {
+            T[k - 1] = hcol[k - 1];                             // H[k,k]
+            if (k >= 2) T[2 * p.ncol + (k - 2)] = hcol[k - 2];  // H[k-1,k] keeps the MGS value; H[1:k-2,k] .= 0 (:129)
+            T[p.ncol + (k - 1)] = hcol[k];                      // beta = H[k+1,k] (:127)
+            T[2 * p.ncol + (k - 1)] = hcol[k];                  // update_subdiagonals! (:137)
+            p.fallbacks[s] += 1;
+        }
+        // Gram row of the replaced column (v holds the new v_{k+1})
+        const double* Vs = p.V + (long long)s * p.vstride;
+        off2 = 0.0;
+        for (int j = 0; j <= newcol; ++j) {
+            const double* col = Vs + (long long)j * p.ldv;
+            acc = 0.0;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) acc = fma(v[i], col[i], acc);
+            const double gj = block_sum(acc, scratch);
+            if (threadIdx.x == 0) g[j] = gj;
+            if (j < newcol) off2 = fma(gj, gj, off2);
+            else dd = gj - 1.0;
+        }
+        Snew = p.S[s] + 2.0 * off2 + dd * dd;
+    }
+    if (threadIdx.x == 0) {
+        p.S[s] = Snew;
+        if (s == p.mode0_local) p.orthS[newcol] = Snew;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Arnoldi step k for every mode: one CTA per mode runs the two-pass MGS and stores column k of
+// the Hessenberg matrix.  Algorithmic HBM bytes per mode: (16 k + 8 (ndiag + 3)) n.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) arnoldi_mgs_kernel(KrylovParams p, int k, double* vscratch) {
+    if (*p.status != ST_RUNNING) return;
+    extern __shared__ double smem[];
+    __shared__ double scratch[32];
+    const int s = blockIdx.x;
+    double* hcol = smem;
+    double* v = vscratch ? vscratch + (long long)s * p.ldv : smem + p.ncol;
+    mgs_step_cta(p, s, k, v, hcol, scratch);
+    double* Hs = p.Hd + (long long)s * p.ncol * p.ncol + (long long)(k - 1) * p.ncol;  // column k
+    for (int c = threadIdx.x; c <= k; c += blockDim.x) Hs[c] = hcol[c];
+    if (threadIdx.x == 0) {
+        double* T = p.T + (long long)s * 3 * p.ncol;
+        T[k - 1] = hcol[k - 1];
+        T[p.ncol + (k - 1)] = hcol[k];  // H[k+1,k], read by the residual's boundary term
+    }
+}
+
+}  // namespace tk

@@ -1,0 +1,393 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on the same inputs.
+
+Tolerances: Krylov coefficients, Ritz values, b~, ||Hy||^2, <Hy,b>, ||b~||^2 and the
+boundary term to 1e-11 relative; r_comp to 1e-11 ABSOLUTE relative to the magnitude of the three terms it
+is the cancellation of; the relative residual to 1e-11 while r_comp is well conditioned.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-11
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def make_solver(tk, A_list, b_list, nmax, variant, instance, cls, flags=None, tol=1e-8, schedule=True):
+    d, n = len(A_list), A_list[0].shape[0]
+    flags = tk.TK_FLAG_REFERENCE_H1 if flags is None else flags
+    s = tk.Solver(d, n, nmax, instance, cls, variant, flags=flags)
+    s.set_operators(A_list)
+    s.set_rhs(b_list)
+    if schedule:
+        s.set_schedule(A_list[0], tol)
+    return s
+
+
+# ---------------------------------------------------------------------------------------------
+# kernel (2): batched symmetric tridiagonal eigensolver
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 31, 32, 33, 64, 100, 130, 200, 256])
+def test_tridiag_eig(tk, gpu, k):
+    rng = np.random.default_rng(k)
+    nb = 3
+    diag = rng.normal(size=(nb, k)) * 1e3
+    sub = rng.normal(size=(nb, max(k - 1, 0))) * 1e3
+    # one Lanczos-like problem: Jacobi matrix of the scaled 1D Laplacian
+    diag[0] = 2.0e8
+    if k > 1:
+        sub[0] = -1.0e8
+    theta, Q = tk.tridiag_eig_batched(diag, sub)
+    for p in range(nb):
+        T = np.diag(diag[p]) + np.diag(sub[p], -1) + np.diag(sub[p], 1) if k > 1 else np.diag(diag[p])
+        w = np.linalg.eigvalsh(T)
+        nT = np.abs(T).sum(axis=1).max()
+        assert np.max(np.abs(np.sort(theta[p]) - w)) <= 1e-13 * nT
+        assert np.linalg.norm(Q[p].T @ Q[p] - np.eye(k)) <= 1e-13 * max(k, 4)
+        assert np.linalg.norm(T @ Q[p] - Q[p] * theta[p]) <= 2e-13 * nT * max(np.sqrt(k), 1)
+
+
+def test_tridiag_eig_clustered_and_split(tk, gpu):
+    """Zero sub-diagonals (decoupled blocks) and tight clusters (Wilkinson-like), which ghost Ritz values produce."""
+    k = 41
+    diag = np.abs(np.arange(k) - k // 2).astype(float)[None, :]     # Wilkinson W21+-like
+    sub = np.ones((1, k - 1))
+    sub[0, 10] = 0.0
+    sub[0, 25] = 1e-300
+    theta, Q = tk.tridiag_eig_batched(diag, sub)
+    T = np.diag(diag[0]) + np.diag(sub[0], -1) + np.diag(sub[0], 1)
+    assert np.max(np.abs(np.sort(theta[0]) - np.linalg.eigvalsh(T))) < 1e-13 * 40
+    assert np.linalg.norm(Q[0].T @ Q[0] - np.eye(k)) < 1e-12
+    assert np.linalg.norm(T @ Q[0] - Q[0] * theta[0]) < 1e-12 * 40
+
+
+# ---------------------------------------------------------------------------------------------
+# kernels (1): Krylov steps against the oracle, step by step
+# ---------------------------------------------------------------------------------------------
+def _compare_bases(tk, orc, slv, S, d, nmax, hessenberg=False):
+    for s in range(d):
+        H = slv.get_H(s)
+        k = nmax
+        Hk, Ho = H[: k + 1, :k], S.H[s][: k + 1, :k]
+        assert rel(Hk, Ho) < RTOL, f"H mode {s}"
+        bt = slv.get_bt(s)
+        assert rel(bt[: k + 1], np.r_[S.bt[s][:k], S.V[s][:, k] @ S.b[s]]) < RTOL
+        for col in (1, 2, k // 2, k + 1):
+            v = slv.get_V(s, col)
+            assert np.max(np.abs(v - S.V[s][:, col - 1])) < 1e-10, f"V mode {s} col {col}"
+
+
+@pytest.mark.parametrize("n,nmax", [(200, 40), (257, 20), (1000, 64)])
+def test_lanczos_ttr_steps(tk, orc, tables, gpu, n, nmax):
+    """TensorLanczos, distinct right-hand sides per mode (test/decompositions.jl:21-56 setup)."""
+    d = 4
+    rng = np.random.default_rng(n)
+    A = tk.assemble_matrix(n, tk.Laplace)
+    b = orc.normalize_rhs([rng.random(n) for _ in range(d)])
+    slv = make_solver(tk, [A] * d, b, nmax, tk.TensorLanczos, tk.SymInstance, tk.Laplace)
+    slv.begin()
+    Ao = orc.assemble_matrix(n, orc.LAPLACE)
+    S = orc.OracleSolve([Ao] * d, b, 1e-8, nmax, orc.LANCZOS, orc.SYM, orc.LAPLACE, tables)
+    for k in range(2, nmax + 1):
+        slv.step_bases(k)
+        for s in range(d):
+            S._step(s, k)
+            S.bt[s][k - 1] = S.V[s][:, k - 1] @ S.b[s]
+    _compare_bases(tk, orc, slv, S, d, nmax)
+    # isposdef(H_s[1:k,1:k]) and orthonormality, test/decompositions.jl:36-55 (k = 50 there)
+    H = slv.get_H(0)[:nmax, :nmax]
+    assert np.linalg.eigvalsh(np.tril(H) + np.tril(H, -1).T).min() > 0
+    slv.close()
+
+
+def test_lanczos_reorth_fallback(tk, orc, tables, gpu):
+    """LanczosReorth on the clustered EigValMat spectrum: orthogonality is lost quickly, the monitor must fire the
+    MGS fallback and leave H[k-1,k] un-symmetric exactly as the reference does (orthogonal_bases.jl:119-131)."""
+    d, n, nmax = 2, 200, 110
+    ev = np.array([(j * j) * (1.0 / (n * n)) for j in range(1, n + 1)])
+    A = sp.diags([ev], [0]).tocsc()
+    b = orc.normalize_rhs([golden("eigval_dzero")["rhs_d5"]] * d)
+    slv = make_solver(tk, [A] * d, b, nmax, tk.TensorLanczosReorth, tk.SymInstance, tk.EigValMat, schedule=False)
+    slv.begin()
+    Ao = sp.diags([ev], [0]).tocsr()
+    S = orc.OracleSolve([Ao] * d, b, 1e-8, nmax, orc.LANCZOS_REORTH, orc.SYM, orc.EIGVALMAT, tables)
+    fired_at = []
+    for k in range(2, nmax + 1):
+        before = S.stats.get("fallbacks", 0)
+        slv.step_bases(k)
+        for s in range(d):
+            S._step(s, k)
+        if S.stats.get("fallbacks", 0) > before:
+            fired_at.append(k)
+    assert len(fired_at) > 0, "the test problem must exercise the fallback"
+    _, fb = slv.orth_state(0)
+    # the trigger compares a noise-level loss with sqrt(eps); allow the count to differ by a few
+    assert abs(fb - len(fired_at)) <= max(3, len(fired_at) // 5)
+    for s in range(d):
+        H = slv.get_H(s)
+        Ho = S.H[s]
+        kk = fired_at[0] - 1        # before the first fallback everything agrees to rounding
+        assert rel(H[:kk, :kk], Ho[:kk, :kk]) < RTOL
+        # afterwards the bases stay orthonormal to the monitor's threshold
+        V = np.stack([slv.get_V(s, c) for c in range(1, nmax + 1)], axis=1)
+        assert np.linalg.norm(V.T @ V - np.eye(nmax)) < 5e-8
+        Sg, _ = slv.orth_state(s)
+        Vall = np.stack([slv.get_V(s, c) for c in range(1, nmax + 2)], axis=1)
+        assert np.sqrt(Sg) == pytest.approx(np.linalg.norm(Vall.T @ Vall - np.eye(nmax + 1)), rel=1e-3, abs=1e-12)
+    slv.close()
+
+
+def test_reorth_forced_fallback_matches_oracle(tk, orc, tables, gpu):
+    """Deterministic fallback check: on a tiny problem the fallback fires at the same k in both implementations
+    and the resulting (un-symmetric) H agrees entry by entry."""
+    d, n, nmax = 1, 40, 39
+    ev = np.array([(j * j) * (1.0 / (n * n)) for j in range(1, n + 1)])
+    A = sp.diags([ev], [0]).tocsc()
+    rng = np.random.default_rng(5)
+    b = orc.normalize_rhs([rng.random(n)])
+    slv = make_solver(tk, [A], b, nmax, tk.TensorLanczosReorth, tk.SymInstance, tk.EigValMat, schedule=False)
+    slv.begin()
+    S = orc.OracleSolve([A.tocsr()], b, 1e-8, nmax, orc.LANCZOS_REORTH, orc.SYM, orc.EIGVALMAT, tables)
+    first = None
+    for k in range(2, nmax + 1):
+        before = S.stats.get("fallbacks", 0)
+        slv.step_bases(k)
+        S._step(0, k)
+        _, fb = slv.orth_state(0)
+        if first is None and (S.stats.get("fallbacks", 0) > before or fb > 0):
+            first = k
+            assert S.stats.get("fallbacks", 0) == 1 and fb == 1, "first fallback at different iterations"
+            H, Ho = slv.get_H(0), S.H[0]
+            assert rel(H[: k + 1, :k], Ho[: k + 1, :k]) < 1e-9
+            assert H[k - 2, k - 1] != H[k - 1, k - 2]      # the reference's asymmetric leftover
+            break
+    assert first is not None
+    slv.close()
+
+
+@pytest.mark.parametrize("cls_name,n,nmax", [("ConvDiff", 200, 30), ("ConvDiff", 513, 24)])
+def test_arnoldi_steps(tk, orc, gpu, cls_name, n, nmax):
+    d = 3
+    rng = np.random.default_rng(11)
+    A = tk.assemble_matrix(n, tk.ConvDiff)
+    b = orc.normalize_rhs([rng.random(n) for _ in range(d)])
+    s = tk.Solver(d, n, nmax, tk.NonSymInstance, tk.ConvDiff, tk.TensorArnoldi)
+    s.set_operators([A] * d)
+    s.set_rhs(b)
+    s.begin()
+    Ao = orc.assemble_matrix(n, orc.CONVDIFF)
+    S = orc.OracleSolve([Ao] * d, b, 1e-8, nmax, orc.ARNOLDI, orc.NONSYM, orc.CONVDIFF, None,
+                        schedule={k: None for k in range(2, nmax + 1)})
+    for k in range(2, nmax + 1):
+        s.step_bases(k)
+        for m in range(d):
+            S._step(m, k)
+            S.bt[m][k - 1] = S.V[m][:, k - 1] @ S.b[m]
+    _compare_bases(tk, orc, s, S, d, nmax)
+    s.close()
+
+
+def test_csr_and_dense_operators(tk, orc, tables, gpu):
+    """General sparse (more than 9 diagonals -> CSR path) and dense symmetric operators give the same Lanczos
+    coefficients as the oracle."""
+    n, nmax, d = 150, 25, 2
+    rng = np.random.default_rng(21)
+    R = sp.random(n, n, density=0.08, random_state=3, format="csr")
+    Asp = (R + R.T + sp.diags([np.full(n, 20.0)], [0])).tocsc()
+    Ad = Asp.toarray()
+    b = orc.normalize_rhs([rng.random(n) for _ in range(d)])
+    for M in (Asp, Ad):
+        slv = make_solver(tk, [M] * d, b, nmax, tk.TensorLanczos, tk.SymInstance, tk.RandSPD, schedule=False)
+        slv.begin()
+        S = orc.OracleSolve([sp.csr_matrix(Ad)] * d, b, 1e-8, nmax, orc.LANCZOS, orc.SYM, orc.RANDSPD, tables,
+                            schedule={k: None for k in range(2, nmax + 1)})
+        for k in range(2, nmax + 1):
+            slv.step_bases(k)
+            for s in range(d):
+                S._step(s, k)
+                S.bt[s][k - 1] = S.V[s][:, k - 1] @ S.b[s]
+        _compare_bases(tk, orc, slv, S, d, nmax)
+        slv.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# kernels (3) (4): compressed solve + residual, iteration by iteration
+# ---------------------------------------------------------------------------------------------
+def _check_iteration(out, ref, k):
+    for key in ("hy2", "hyb", "bb", "boundary"):
+        assert out[key] == pytest.approx(ref[key], rel=RTOL), f"{key} at k={k}"
+    scale = abs(ref["hy2"]) + 2 * abs(ref["hyb"]) + abs(ref["bb"])
+    assert abs(out["r_comp"] - ref["r_comp"]) <= RTOL * scale, f"r_comp at k={k}"
+    assert out["t"] == ref["t"] and out["lambda_min"] == pytest.approx(ref["lambda_min"], rel=1e-15)
+
+
+@pytest.mark.parametrize("d,n,nmax,per_mode", [(5, 200, 30, False), (3, 120, 20, True), (17, 300, 16, False),
+                                               (40, 128, 12, True)])
+def test_compress_and_residual_phases(tk, orc, tables, gpu, d, n, nmax, per_mode):
+    rng = np.random.default_rng(d * 1000 + n)
+    A = tk.assemble_matrix(n, tk.Laplace)
+    if per_mode:
+        b = orc.normalize_rhs([rng.random(n) for _ in range(d)])
+    else:
+        one = rng.random(n)
+        b = orc.normalize_rhs([one] * d)
+    flags = 0 if per_mode else tk.TK_FLAG_REFERENCE_H1
+    slv = make_solver(tk, [A] * d, b, nmax, tk.TensorLanczosReorth, tk.SymInstance, tk.Laplace, flags=flags)
+    slv.begin()
+    Ao = orc.assemble_matrix(n, orc.LAPLACE)
+    S = orc.OracleSolve([Ao] * d, b, 1e-8, nmax, orc.LANCZOS_REORTH, orc.SYM, orc.LAPLACE, tables, per_mode=per_mode,
+                        ignore_breakdown=True)
+    for k in range(2, nmax + 1):
+        slv.step_bases(k)
+        slv.compress(k)
+        out = slv.residual(k, 0.0)
+        S.iterate()
+        _check_iteration(out, S.detail[k], k)
+        if k in (2, nmax):
+            for s in (0, d - 1):
+                Y = slv.get_Y(s, k)
+                assert rel(Y, S.lastY[s]) < 1e-10
+            th, Q = slv.get_eig(0, k)
+            Hk = S.H[0][:k, :k]
+            Hs = np.tril(Hk) + np.tril(Hk, -1).T
+            assert rel(np.sort(th), np.linalg.eigvalsh(Hs)) < 1e-13
+            assert np.linalg.norm(Hs @ Q - Q * th) < 1e-12 * np.abs(Hs).max() * k
+    slv.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# whole solves through the reference-shaped API
+# ---------------------------------------------------------------------------------------------
+def test_solve_matches_reference_history_laplace_d5(tk, gpu):
+    """The reference's own stored run (Julia, laplace_new d=5, tol 1e-9, nmax 199): same relative residuals."""
+    g = golden("laplace_new")
+    d, n, nmax = 5, 200, 199
+    A = tk.KroneckerMatrix.gallery(tk.SymInstance, d, n, tk.Laplace)
+    system = tk.TensorizedSystem(tk.SymInstance, A, [g["rhs_d5"]] * d)
+    cd = tk.solve_tensorized_system(system, nmax, tk.TensorLanczosReorth, 1e-9, verbose=False)
+    rr, pr = g["relres_d5"], g["projres_d5"]
+    assert cd.status == tk.TK_NMAX and cd.niterations == 199 and len(rr) == 199
+    k = np.arange(2, 61)
+    assert np.max(np.abs(cd.relative_residual_norm[k - 1] - rr[k - 1]) / rr[k - 1]) < 1e-10
+    k = np.arange(61, 151)
+    assert np.max(np.abs(cd.relative_residual_norm[k - 1] - rr[k - 1]) / rr[k - 1]) < 1e-6
+    assert cd.relative_residual_norm[0] == 1.0 and cd.projected_residual_norm[0] == 1.0
+    assert np.max(np.abs(cd.projected_residual_norm[1:60] - pr[1:60]) / pr[1:60]) < 1e-9
+    assert np.all(cd.orthogonality_data[1:] < 1e-8)
+
+
+@pytest.mark.parametrize("d", [10, 50])
+def test_solve_matches_reference_history_laplace_more_modes(tk, gpu, d):
+    g = golden("laplace_new")
+    n, nmax = 200, 40
+    A = tk.KroneckerMatrix.gallery(tk.SymInstance, d, n, tk.Laplace)
+    system = tk.TensorizedSystem(tk.SymInstance, A, [g[f"rhs_d{d}"]] * d)
+    cd = tk.solve_tensorized_system(system, nmax, tk.TensorLanczosReorth, 1e-9, verbose=False)
+    rr = g[f"relres_d{d}"]
+    k = np.arange(2, nmax + 1)
+    assert np.max(np.abs(cd.relative_residual_norm[k - 1] - rr[k - 1]) / rr[k - 1]) < 2e-9
+
+
+def test_solve_converges_and_returns_kruskal(tk, orc, tables, gpu):
+    """A configuration that reaches its tolerance (large d, tol 1e-4): status, iteration count, ConvergenceData
+    conventions and the Kruskal solution x = (lambda, V_s Y_s) all match the oracle."""
+    d, n, nmax, tol = 64, 1000, 40, 1e-4
+    b = np.random.default_rng(12345).random(n)
+    A = tk.KroneckerMatrix.gallery(tk.SymInstance, d, n, tk.Laplace)
+    system = tk.TensorizedSystem(tk.SymInstance, A, [b] * d)
+    cd = tk.ConvergenceData(nmax)
+    x = tk.tensorkrylov(cd, system.A, system.b, tol, nmax, tk.TensorLanczosReorth, verbose=False)
+    Ao = orc.assemble_matrix(n, orc.LAPLACE)
+    S = orc.tensorkrylov([Ao] * d, orc.normalize_rhs([b] * d), tol, nmax, orc.LANCZOS_REORTH, orc.SYM, orc.LAPLACE,
+                         tables, fast_solve=True)
+    assert cd.status == S.status
+    if S.status == orc.ST_CONVERGED:
+        assert x is not None and cd.term_k == S.k and cd.niterations == nmax
+        lam, fm = S.x
+        assert rel(x.lambda_, lam) < 1e-13
+        for s in (0, d // 2, d - 1):
+            assert rel(x.fmat[s], fm[s]) < 1e-9
+    elif S.status == orc.ST_BREAKDOWN:
+        assert x is None and cd.niterations == S.niterations and len(cd.relative_residual_norm) == S.niterations
+    kk = np.arange(2, min(S.k, cd.term_k))
+    assert np.max(np.abs(cd.relative_residual_norm[kk - 1] - S.relres[kk - 1]) / S.relres[kk - 1]) < 1e-7
+
+
+def test_true_residual_of_returned_solution(tk, orc, gpu):
+    """d=3, n=12: the returned Kruskal tensor, expanded densely, has exactly the residual the estimator reports
+    (Lemma 3.4 is an identity for the computed y)."""
+    d, n, nmax = 3, 12, 8
+    rng = np.random.default_rng(2)
+    A1 = tk.assemble_matrix(n, tk.Laplace)
+    b = orc.normalize_rhs([rng.random(n) for _ in range(d)])
+    slv = make_solver(tk, [A1] * d, b, nmax, tk.TensorLanczosReorth, tk.SymInstance, tk.Laplace,
+                      flags=tk.TK_FLAG_FIXED_ITERATIONS)
+    res = slv.solve(1e-8)
+    lam, fmat = slv.solution(force=True)
+    x = tk.kroneckervectorize(tk.KruskalTensor(lam, [fmat[s] for s in range(d)]))
+    Ad = orc.kron_sum_dense([A1] * d)
+    bd = orc.kron_vector(b)
+    true = np.linalg.norm(Ad @ x - bd) / np.linalg.norm(bd)
+    assert res["relres"][nmax - 1] == pytest.approx(true, rel=1e-6)
+    slv.close()
+
+
+def test_edge_cases(tk, orc, tables, gpu):
+    # nmax = 1: the loop body never runs -> "No convergence", histories stay ones (convergence.jl:11-20)
+    n = 50
+    A = tk.KroneckerMatrix.gallery(tk.SymInstance, 2, n, tk.Laplace)
+    system = tk.TensorizedSystem(tk.SymInstance, A, tk.random_rhs(2, n, np.random.default_rng(0)))
+    cd = tk.solve_tensorized_system(system, 1, tk.TensorLanczos, 1e-8, verbose=False)
+    assert cd.status == tk.TK_NMAX and np.all(cd.relative_residual_norm == 1.0)
+    # d = 1, odd n, right-hand side with zeros
+    n = 33
+    b = np.zeros(n); b[::3] = 1.0
+    A = tk.KroneckerMatrix.gallery(tk.SymInstance, 1, n, tk.Laplace)
+    system = tk.TensorizedSystem(tk.SymInstance, A, [b])
+    cd = tk.solve_tensorized_system(system, 10, tk.TensorLanczosReorth, 1e-8, verbose=False,
+                                    flags=tk.TK_FLAG_REFERENCE_H1 | tk.TK_FLAG_FIXED_ITERATIONS)
+    Ao = orc.assemble_matrix(n, orc.LAPLACE)
+    S = orc.tensorkrylov([Ao], orc.normalize_rhs([b]), 1e-8, 10, orc.LANCZOS_REORTH, orc.SYM, orc.LAPLACE, tables,
+                         ignore_breakdown=True)
+    assert rel(cd.relative_residual_norm, S.relres) < 1e-9
+    # shape mismatch is rejected like the reference's @assert (system.jl:27-28)
+    with pytest.raises(tk.TKError):
+        s = tk.Solver(2, 20, 5, tk.SymInstance, tk.Laplace, tk.TensorLanczos)
+        try:
+            s.set_rhs([np.ones(21), np.ones(21)])
+        finally:
+            s.close()
+    # solving without inputs fails loudly
+    s = tk.Solver(2, 20, 5, tk.SymInstance, tk.Laplace, tk.TensorLanczos)
+    with pytest.raises(tk.TKError):
+        s.solve(1e-8)
+    s.close()
+
+
+def test_large_modes_property(tk, gpu):
+    """BASELINE-size property test (d=256, n=10^4 slice of C3/C5): identical modes must produce bit-identical
+    Krylov data, the bases stay orthonormal, and b~ = ||b|| e_1 up to the orthogonality loss."""
+    d, n, nmax = 256, 10000, 12
+    b = np.random.default_rng(12345).random(n)
+    A = tk.KroneckerMatrix.gallery(tk.SymInstance, d, n, tk.Laplace)
+    system = tk.TensorizedSystem(tk.SymInstance, A, [b] * d)
+    out = []
+    cd = tk.ConvergenceData(nmax)
+    tk.tensorkrylov(cd, system.A, system.b, 1e-12, nmax, tk.TensorLanczosReorth, verbose=False, solver_out=out,
+                    flags=tk.TK_FLAG_REFERENCE_H1 | tk.TK_FLAG_FIXED_ITERATIONS)
+    slv = out[0]
+    H0, Hl = slv.get_H(0), slv.get_H(d - 1)
+    assert np.array_equal(H0, Hl)
+    V = np.stack([slv.get_V(d - 1, c) for c in range(1, nmax + 2)], axis=1)
+    assert np.linalg.norm(V.T @ V - np.eye(nmax + 1)) < 1e-10
+    bt = slv.get_bt(7)
+    assert bt[0] == pytest.approx(1.0, rel=1e-14) and np.max(np.abs(bt[1:nmax])) < 1e-10
+    assert np.all(np.isfinite(cd.relative_residual_norm)) and cd.relative_residual_norm[nmax - 1] < 1e-3
+    slv.close()
