@@ -53,7 +53,9 @@ enum {
     /* Benchmark mode: never stop on r_comp<0 or on tol; run exactly nmax-1 iterations. */
     TK_FLAG_FIXED_ITERATIONS = 2,
     /* Record CUDA events around the Krylov-step kernels (read with tk_get_timing). */
-    TK_FLAG_TIME_KERNELS = 4
+    TK_FLAG_TIME_KERNELS = 4,
+    /* ... and around every other kernel of the iteration as well. */
+    TK_FLAG_TIME_ALL = 8
 };
 
 enum {
@@ -146,7 +148,8 @@ int tk_tridiag_eig_batched(int32_t device, int32_t nb, int32_t k, const double* 
                            double* theta, double* Q);
 
 /* which: 0 = 3-term Lanczos step, 1 = orthogonality-monitor Gram row, 2 = Arnoldi/MGS step,
- * 3 = eigensolver, 4 = CP assembly + Gram, 5 = cross-mode combine.  Sums over the last tk_solve. */
+ * 3 = eigensolver, 4 = CP assembly + Gram, 5 = cross-mode combine, 6 = the whole last tk_solve
+ * (CUDA events on the handle's stream, first enqueue to last kernel).  Sums over the last tk_solve. */
 int tk_get_timing(tk_handle* h, int32_t which, double* ms_total, int64_t* launches, double* algorithmic_bytes);
 int tk_launch_count(tk_handle* h, int64_t* launches);
 

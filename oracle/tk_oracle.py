@@ -193,10 +193,11 @@ def extreme_eigvals(A1, d, k, instance, cls):
     if cls == LAPLACE:                                              # :335
         return laplace_extremes(d, n, k)
     if cls == RANDSPD:                                              # :337
-        ev = np.linalg.eigvalsh(np.asarray(A1)[:k, :k])
+        M = A1[:k, :k].toarray() if sp.issparse(A1) else np.asarray(A1)[:k, :k]
+        ev = np.linalg.eigvalsh(M)
         return float(ev.min()) * d, float(ev.max()) * d
     if cls == EIGVALMAT:                                            # :339
-        dg = np.diag(np.asarray(A1))[:k]
+        dg = (A1.diagonal() if sp.issparse(A1) else np.diag(np.asarray(A1)))[:k]
         return float(dg.min()) * d, float(dg.max()) * d
     raise TypeError("no extreme_eigvals method for this (instance, class) -- the reference throws MethodError")
 

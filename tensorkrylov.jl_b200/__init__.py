@@ -9,7 +9,7 @@ The directory name contains a dot, so load it with `__graft_entry__.load_package
 (it registers the module as `tensorkrylov_jl_b200`).
 """
 from ._capi import (TK_BREAKDOWN, TK_CONVERGED, TK_FLAG_FIXED_ITERATIONS, TK_FLAG_REFERENCE_H1,  # noqa: F401
-                    TK_FLAG_TIME_KERNELS, TK_NAN, TK_NMAX, TKError, EXPORTS, LIB_PATH, TABLES_PATH,
+                    TK_FLAG_TIME_KERNELS, TK_FLAG_TIME_ALL, TK_NAN, TK_NMAX, TKError, EXPORTS, LIB_PATH, TABLES_PATH,
                     device_count, load_tables)
 from .api import *  # noqa: F401,F403
 from .api import (ConvDiff, ConvergenceData, EigValMat, KronMat, KroneckerMatrix, KruskalTensor, Laplace,  # noqa: F401

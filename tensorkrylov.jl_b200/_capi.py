@@ -21,7 +21,7 @@ TK_SYM, TK_NONSYM = 0, 1
 TK_LAPLACE_DENSE, TK_LAPLACE, TK_CONVDIFF, TK_EIGVALMAT, TK_RANDSPD, TK_GENERIC = 0, 1, 2, 3, 4, 5
 TK_LANCZOS, TK_LANCZOS_REORTH, TK_ARNOLDI = 0, 1, 2
 TK_CONVERGED, TK_NMAX, TK_BREAKDOWN, TK_NAN, TK_RUNNING = 0, 1, 2, 3, -1
-TK_FLAG_REFERENCE_H1, TK_FLAG_FIXED_ITERATIONS, TK_FLAG_TIME_KERNELS = 1, 2, 4
+TK_FLAG_REFERENCE_H1, TK_FLAG_FIXED_ITERATIONS, TK_FLAG_TIME_KERNELS, TK_FLAG_TIME_ALL = 1, 2, 4, 8
 
 EXPORTS = [
     "tk_last_error", "tk_version", "tk_device_count",

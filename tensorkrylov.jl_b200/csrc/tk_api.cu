@@ -142,7 +142,7 @@ struct SchedEntry {
     size_t off = 0;  // into the alpha/omega pools
 };
 
-enum { TM_TTR = 0, TM_GRAM = 1, TM_MGS = 2, TM_EIG = 3, TM_ASM = 4, TM_COMBINE = 5, TM_KINDS = 6 };
+enum { TM_TTR = 0, TM_GRAM = 1, TM_MGS = 2, TM_EIG = 3, TM_ASM = 4, TM_COMBINE = 5, TM_SOLVE = 6, TM_KINDS = 7 };
 
 }  // namespace tk
 
@@ -191,6 +191,7 @@ struct tk_handle {
     struct Timed { int kind; cudaEvent_t a, b; double bytes; };
     std::vector<Timed> timed;
     std::vector<cudaEvent_t> ev_pool;
+    cudaEvent_t ev_solve[2] = {nullptr, nullptr};
     size_t ev_used = 0;
     double tm_ms[TM_KINDS] = {0}, tm_bytes[TM_KINDS] = {0};
     long long tm_launches[TM_KINDS] = {0};
@@ -227,7 +228,8 @@ static cudaEvent_t next_event(tk_handle* h) {
 struct TimedScope {
     tk_handle* h; int kind; cudaEvent_t a = nullptr; double bytes;
     TimedScope(tk_handle* h_, int kind_, double bytes_) : h(h_), kind(kind_), bytes(bytes_) {
-        if (h->flags & TK_FLAG_TIME_KERNELS) { a = next_event(h); cudaEventRecord(a, h->stream); }
+        const bool on = (h->flags & TK_FLAG_TIME_ALL) || ((h->flags & TK_FLAG_TIME_KERNELS) && kind <= TM_MGS);
+        if (on) { a = next_event(h); cudaEventRecord(a, h->stream); }
     }
     ~TimedScope() {
         if (a) { cudaEvent_t b = next_event(h); cudaEventRecord(b, h->stream); h->timed.push_back({kind, a, b, bytes}); }
@@ -660,7 +662,7 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
 
     TK_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     const size_t dl = std::max(h->dl, 1);
-    TK_TRY(h->V.alloc(dl * (size_t)h->ncol * h->ldv));
+    TK_TRY(h->V.alloc(dl * (size_t)h->ncol * h->ldv, false));
     TK_TRY(h->b.alloc(dl * (size_t)h->ldv));
     TK_TRY(h->T.alloc(dl * 3 * (size_t)h->ncol));
     if (variant == TK_ARNOLDI) TK_TRY(h->Hd.alloc(dl * (size_t)h->ncol * h->ncol));
@@ -703,6 +705,7 @@ void tk_destroy(tk_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (auto e : h->ev_pool) cudaEventDestroy(e);
+    for (auto e : h->ev_solve) if (e) cudaEventDestroy(e);
     for (auto e : h->ring_ev) cudaEventDestroy(e);
     if (h->status_ring) cudaFreeHost(h->status_ring);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -916,6 +919,8 @@ int tk_solve(tk_handle* h, double tol, int32_t* status, int64_t* niter, int32_t*
     TK_CUDA(cudaSetDevice(h->device));
     TK_TRY(upload_schedule(h));
     TK_TRY(alloc_work(h));
+    if (!h->ev_solve[0]) { TK_CUDA(cudaEventCreate(&h->ev_solve[0])); TK_CUDA(cudaEventCreate(&h->ev_solve[1])); }
+    TK_CUDA(cudaEventRecord(h->ev_solve[0], h->stream));
     TK_TRY(begin_solve(h));
     const int LAG = 3, RING = 8;
     int st = ST_RUNNING;
@@ -932,6 +937,7 @@ int tk_solve(tk_handle* h, double tol, int32_t* status, int64_t* niter, int32_t*
         TK_CUDA(cudaMemcpyAsync(&h->status_ring[slot], h->status_d.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         TK_CUDA(cudaEventRecord(h->ring_ev[slot], h->stream));
     }
+    TK_CUDA(cudaEventRecord(h->ev_solve[1], h->stream));
     TK_CUDA(cudaStreamSynchronize(h->stream));
     int tk_ = 0, eigfail = 0;
     long long nit = 0;
@@ -944,6 +950,11 @@ int tk_solve(tk_handle* h, double tol, int32_t* status, int64_t* niter, int32_t*
     if (projres) TK_CUDA(cudaMemcpy(projres, h->projres_d.p, 8 * (size_t)h->nmax, cudaMemcpyDeviceToHost));
     if (orth) TK_CUDA(cudaMemcpy(orth, h->orth_d.p, 8 * (size_t)h->nmax, cudaMemcpyDeviceToHost));
     TK_TRY(collect_timing(h));
+    {
+        float ms = 0.f;
+        TK_CUDA(cudaEventElapsedTime(&ms, h->ev_solve[0], h->ev_solve[1]));
+        h->tm_ms[TM_SOLVE] = ms; h->tm_launches[TM_SOLVE] = 1;
+    }
     if (status) *status = st;
     if (niter) *niter = nit;
     if (term_k) *term_k = tk_;
