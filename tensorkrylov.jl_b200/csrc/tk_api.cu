@@ -154,7 +154,9 @@ struct tk_handle {
     long long ldv = 0;
     int per_mode = 0, ncls = 1;
     int chunk_modes = 16, nchunks = 1, chunk_base = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;    // Krylov-step kernels (1)
+    cudaStream_t stream2 = nullptr;   // compressed solve + residual (2)-(4): runs one iteration behind, concurrently
+    std::vector<cudaEvent_t> step_ev;  // step k done on `stream` -> `stream2` may start iteration k
     ncclComm_t comm = nullptr;
 
     // Krylov state
@@ -209,6 +211,12 @@ struct tk_handle {
 
 namespace tk {
 
+// developer knobs for kernel tuning experiments (unset in production)
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
 static int check_mode(const tk_handle* h, int s, bool* local) {
     if (!h) return set_error(TK_EINVAL, "null handle");
     if (s < 0 || s >= h->d) return set_error(TK_EINVAL, "mode %d out of range [0,%d)", s, h->d);
@@ -226,13 +234,13 @@ static cudaEvent_t next_event(tk_handle* h) {
 }
 
 struct TimedScope {
-    tk_handle* h; int kind; cudaEvent_t a = nullptr; double bytes;
-    TimedScope(tk_handle* h_, int kind_, double bytes_) : h(h_), kind(kind_), bytes(bytes_) {
+    tk_handle* h; int kind; cudaEvent_t a = nullptr; double bytes; cudaStream_t st;
+    TimedScope(tk_handle* h_, int kind_, double bytes_, cudaStream_t st_) : h(h_), kind(kind_), bytes(bytes_), st(st_) {
         const bool on = (h->flags & TK_FLAG_TIME_ALL) || ((h->flags & TK_FLAG_TIME_KERNELS) && kind <= TM_MGS);
-        if (on) { a = next_event(h); cudaEventRecord(a, h->stream); }
+        if (on) { a = next_event(h); cudaEventRecord(a, st); }
     }
     ~TimedScope() {
-        if (a) { cudaEvent_t b = next_event(h); cudaEventRecord(b, h->stream); h->timed.push_back({kind, a, b, bytes}); }
+        if (a) { cudaEvent_t b = next_event(h); cudaEventRecord(b, st); h->timed.push_back({kind, a, b, bytes}); }
     }
 };
 
@@ -334,15 +342,21 @@ static int launch_ttr_t(tk_handle* h, int k, int threads, size_t smem) {
 }
 
 static int launch_ttr(tk_handle* h, int k) {
-    // split a mode over a cluster when there are too few modes to fill 148 SMs, or the slice would not fit in smem
+    const double bytes = (op_bytes_per_row(h) + 32.0) * (double)h->n * h->dl;
+    TimedScope ts(h, TM_TTR, bytes, h->stream);
+    // CTAs per mode (one cluster): at least 2 whenever a slice keeps >= 2048 rows (measured best on B200 at
+    // n = 10^4), more when the modes alone cannot fill the machine or a slice would not fit in shared memory
     int cpm = 1;
-    while (cpm < 8 && ((long long)h->dl * cpm < 296 || (size_t)h->n * 8 / cpm > smem_limit(h)) && h->n / (cpm * 2) >= 256) cpm *= 2;
+    while (cpm < 8 && ((size_t)h->n * 8 / cpm > smem_limit(h) ||
+                       (h->n / (2 * cpm) >= 2048 && cpm < 2) ||
+                       (h->n / (2 * cpm) >= 512 && (long long)h->dl * cpm < 296)))
+        cpm *= 2;
+    if (env_int("TK_TTR_CPM", 0)) cpm = env_int("TK_TTR_CPM", 0);
     const int chunk = (((h->n + cpm - 1) / cpm) + 1) & ~1;
     const size_t smem = (size_t)chunk * 8;
     if (smem > smem_limit(h)) return set_error(TK_EUNSUPPORTED, "n = %d is too large for the 3-term step kernel", h->n);
-    const int threads = chunk >= 2048 ? 512 : 256;
-    const double bytes = (op_bytes_per_row(h) + 32.0) * (double)h->n * h->dl;
-    TimedScope ts(h, TM_TTR, bytes);
+    int threads = chunk >= 2048 ? 512 : 256;
+    if (env_int("TK_TTR_THREADS", 0)) threads = env_int("TK_TTR_THREADS", 0);
     switch (cpm) {
         case 1: return launch_ttr_t<1>(h, k, threads, smem);
         case 2: return launch_ttr_t<2>(h, k, threads, smem);
@@ -354,17 +368,37 @@ static int launch_ttr(tk_handle* h, int k) {
 // Gram row of the newest column for `nmodes` modes starting at local mode `base`
 static int launch_gram(tk_handle* h, int ncols, int base, int nmodes) {
     if (nmodes <= 0) return 0;
-    const bool w_smem = (size_t)h->n * 8 <= 160 * 1024;
-    // enough CTAs to fill the machine twice over, at most 16 columns per CTA, columns spread evenly
-    long long want = ((long long)ncols * nmodes + 591) / 592;
-    int cpc = (int)std::min<long long>(16, std::max<long long>(1, want));
-    int nchunks = (ncols + cpc - 1) / cpc;
-    cpc = (ncols + nchunks - 1) / nchunks;
-    const size_t smem = w_smem ? (size_t)h->n * 8 : 0;
-    TK_TRY(allow_smem(gram_row_kernel, smem));
+    const int threads = env_int("TK_GRAM_THREADS", 256) == 512 ? 512 : 256, nwarp = threads / 32;
+    // warps per column: long columns are cut into segments so all warps of a CTA stream the same amount
+    int wpc = h->n >= 8192 ? 8 : h->n >= 4096 ? 4 : h->n >= 2048 ? 2 : 1;
+    if (env_int("TK_GRAM_WPC", 0)) wpc = env_int("TK_GRAM_WPC", 0);
+    wpc = std::min(wpc, nwarp);
+    const int maxcpc = env_int("TK_GRAM_CPC", 32);
+    const int gran = nwarp / wpc;                    // columns a CTA processes per pass
+    // <= maxcpc columns per CTA (the new vector is re-staged once per CTA); more chunks when there are few modes
+    int nchunks = (ncols + maxcpc - 1) / maxcpc;
+    const long long want = (592 + nmodes - 1) / nmodes;
+    nchunks = (int)std::max<long long>(nchunks, std::min<long long>(want, (ncols + gran - 1) / gran));
+    int cpc = (ncols + nchunks - 1) / nchunks;
+    nchunks = (ncols + cpc - 1) / cpc;
+    size_t smem = (size_t)cpc * GRAM_PSTRIDE * 8 + (size_t)h->n * 8;
+    const bool w_smem = smem <= smem_limit(h);
+    if (!w_smem) smem = (size_t)cpc * GRAM_PSTRIDE * 8;
     const double bytes = 8.0 * (double)h->n * (double)ncols * nmodes;
-    TimedScope ts(h, TM_GRAM, bytes);
-    gram_row_kernel<<<dim3(nchunks, nmodes), 256, smem, h->stream>>>(h->kp(), ncols, cpc, base, w_smem ? 1 : 0);
+    const int U = env_int("TK_GRAM_U", 4);
+    TimedScope ts(h, TM_GRAM, bytes, h->stream);
+#define TK_GRAM_LAUNCH(UU, TT)                                                                                   \
+    do {                                                                                                         \
+        TK_TRY(allow_smem(gram_row_kernel<UU, TT>, smem));                                                       \
+        gram_row_kernel<UU, TT><<<dim3(nchunks, nmodes), TT, smem, h->stream>>>(h->kp(), ncols, cpc, base,       \
+                                                                                w_smem ? 1 : 0, wpc);            \
+    } while (0)
+    if (threads == 512) {
+        if (U == 8) TK_GRAM_LAUNCH(8, 512); else if (U == 2) TK_GRAM_LAUNCH(2, 512); else TK_GRAM_LAUNCH(4, 512);
+    } else {
+        if (U == 8) TK_GRAM_LAUNCH(8, 256); else if (U == 2) TK_GRAM_LAUNCH(2, 256); else TK_GRAM_LAUNCH(4, 256);
+    }
+#undef TK_GRAM_LAUNCH
     h->launches++;
     TK_CUDA(cudaGetLastError());
     return 0;
@@ -398,7 +432,7 @@ static int launch_arnoldi(tk_handle* h, int k) {
     TK_TRY(mgs_smem(h, &smem, &vscr));
     TK_TRY(allow_smem(arnoldi_mgs_kernel, smem));
     const double bytes = (16.0 * k + op_bytes_per_row(h) + 24.0) * (double)h->n * h->dl;
-    TimedScope ts(h, TM_MGS, bytes);
+    TimedScope ts(h, TM_MGS, bytes, h->stream);
     arnoldi_mgs_kernel<<<h->dl, 512, smem, h->stream>>>(h->kp(), k, vscr);
     h->launches++;
     TK_CUDA(cudaGetLastError());
@@ -427,15 +461,24 @@ static int enqueue_step_bases(tk_handle* h, int k) {
 
 static int launch_eig(const double* T, long long tstride, int ncol, int k, int nprob, double* theta,
                       int thstride, double* Q, long long qstride, int ldq, const int* status, int* fail, cudaStream_t st) {
-    const int threads = std::min(1024, ((k + 31) / 32) * 32);
-    if (k > 1024) return set_error(TK_EUNSUPPORTED, "eigensolver supports k <= 1024");
-    const int nwarp = threads / 32;
-    size_t base = (size_t)nwarp * 2 * k * 8;
-    size_t full = base + (size_t)k * (k | 1) * 8;
-    const bool q_smem = full <= 200 * 1024;
-    const size_t smem = q_smem ? full : base;
+    if (k > 2048) return set_error(TK_EUNSUPPORTED, "eigensolver supports k <= 2048");
+    // rows of Q per CTA: as many as fit in shared memory next to the per-warp (d, e) copies
+    const size_t budget = 200 * 1024;
+    int rows = std::min(256, ((k + 31) / 32) * 32);
+    while (rows > 8) {
+        const int nwarp = (rows + 31) / 32;
+        const int ldz = rows >= 32 ? rows : rows;
+        if ((size_t)nwarp * 2 * k * 8 + (size_t)k * ldz * 8 <= budget) break;
+        rows = rows > 32 ? rows - 32 : rows / 2;
+    }
+    const int nwarp = (rows + 31) / 32;
+    const int ldz = rows;
+    const size_t smem = (size_t)nwarp * 2 * k * 8 + (size_t)k * ldz * 8;
+    if (smem > budget) return set_error(TK_EUNSUPPORTED, "eigensolver: k = %d does not fit", k);
     TK_TRY(allow_smem(tridiag_eig_kernel, smem));
-    tridiag_eig_kernel<<<nprob, threads, smem, st>>>(T, tstride, ncol, k, theta, thstride, Q, qstride, ldq, q_smem ? 1 : 0, status, fail);
+    const int nrb = (k + rows - 1) / rows;
+    tridiag_eig_kernel<<<dim3(nprob, nrb), nwarp * 32, smem, st>>>(T, tstride, ncol, k, rows, ldz, theta, thstride, Q, qstride,
+                                                                 ldq, status, fail);
     TK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -466,21 +509,21 @@ static int enqueue_compress(tk_handle* h, int k) {
     long long tstride = 3LL * h->ncol;
     if (!h->per_mode && h->world > 1) {
         // the reference exponentiates H_1 for every mode: ship mode 1's tridiagonal to all ranks
-        TK_NCCL(g_nccl.Broadcast(h->T.p, h->Tq.p, 3 * (size_t)h->ncol, ncclDouble, 0, h->comm, h->stream));
+        TK_NCCL(g_nccl.Broadcast(h->T.p, h->Tq.p, 3 * (size_t)h->ncol, ncclDouble, 0, h->comm, h->stream2));
         Tsrc = h->Tq.p;
     }
     {
-        TimedScope ts(h, TM_EIG, 0.0);
+        TimedScope ts(h, TM_EIG, 0.0, h->stream2);
         TK_TRY(launch_eig(Tsrc, tstride, h->ncol, k, h->ncls, h->theta.p, h->ncol, h->Q.p, (long long)h->ldq * h->ldq,
-                          h->ldq, h->status_d.p, h->eigfail_d.p, h->stream));
+                          h->ldq, h->status_d.p, h->eigfail_d.p, h->stream2));
         h->launches++;
     }
     CompressParams c = make_cp(h, k);
     const size_t smem = ((size_t)2 * k + (size_t)k * ASM_TJ) * 8;
     TK_TRY(allow_smem(assemble_cp_kernel, smem));
     {
-        TimedScope ts(h, TM_ASM, 0.0);
-        assemble_cp_kernel<<<h->dl, 256, smem, h->stream>>>(c);
+        TimedScope ts(h, TM_ASM, 0.0, h->stream2);
+        assemble_cp_kernel<<<h->dl, 256, smem, h->stream2>>>(c);
         h->launches++;
         TK_CUDA(cudaGetLastError());
     }
@@ -492,21 +535,21 @@ static int enqueue_compress(tk_handle* h, int k) {
 static int enqueue_residual(tk_handle* h, int k, double tol) {
     CompressParams c = make_cp(h, k);
     {
-        TimedScope ts(h, TM_ASM, 0.0);
-        gram_blocks_kernel<<<h->dl, 256, 0, h->stream>>>(c);
+        TimedScope ts(h, TM_ASM, 0.0, h->stream2);
+        gram_blocks_kernel<<<h->dl, 256, 0, h->stream2>>>(c);
         h->launches++;
         TK_CUDA(cudaGetLastError());
     }
     const long long pst = 5LL * c.t * c.t + 2LL * c.t + 8;
-    TimedScope ts(h, TM_COMBINE, 0.0);
-    combine_chunk_kernel<<<h->nchunks, 256, 0, h->stream>>>(c, h->dl, h->chunk_modes, h->chunk_base, h->partials.p, pst,
+    TimedScope ts(h, TM_COMBINE, 0.0, h->stream2);
+    combine_chunk_kernel<<<h->nchunks, 256, 0, h->stream2>>>(c, h->dl, h->chunk_modes, h->chunk_base, h->partials.p, pst,
                                                             h->orthS.p, (h->first == 0 && h->dl > 0) ? 0 : -1);
     h->launches++;
     TK_CUDA(cudaGetLastError());
     const double* parts = h->partials.p;
     int nparts = h->nchunks;
     if (h->world > 1) {
-        TK_NCCL(g_nccl.AllGather(h->partials.p, h->gathered.p, (size_t)h->nchunks * pst, ncclDouble, h->comm, h->stream));
+        TK_NCCL(g_nccl.AllGather(h->partials.p, h->gathered.p, (size_t)h->nchunks * pst, ncclDouble, h->comm, h->stream2));
         parts = h->gathered.p;
         nparts = h->nchunks * h->world;
     }
@@ -518,7 +561,7 @@ static int enqueue_residual(tk_handle* h, int k, double tol) {
     f.bnorm = h->bnorm_d.p;
     f.relres = h->relres_d.p; f.projres = h->projres_d.p; f.orth = h->orth_d.p; f.detail = h->detail_d.p;
     f.status = h->status_d.p; f.niter = h->niter_d.p; f.term_k = h->term_k_d.p;
-    finalize_kernel<<<1, 256, 0, h->stream>>>(f);
+    finalize_kernel<<<1, 256, 0, h->stream2>>>(f);
     h->launches++;
     TK_CUDA(cudaGetLastError());
     return 0;
@@ -661,6 +704,10 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
     h->ncls = h->per_mode ? std::max(h->dl, 1) : 1;
 
     TK_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    if (env_int("TK_SINGLE_STREAM", 0)) h->stream2 = h->stream;
+    else TK_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    h->step_ev.resize(8);
+    for (auto& e : h->step_ev) TK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     const size_t dl = std::max(h->dl, 1);
     TK_TRY(h->V.alloc(dl * (size_t)h->ncol * h->ldv, false));
     TK_TRY(h->b.alloc(dl * (size_t)h->ldv));
@@ -703,12 +750,15 @@ void tk_destroy(tk_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->stream2) cudaStreamSynchronize(h->stream2);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     for (auto e : h->ev_solve) if (e) cudaEventDestroy(e);
     for (auto e : h->ring_ev) cudaEventDestroy(e);
     if (h->status_ring) cudaFreeHost(h->status_ring);
+    for (auto e : h->step_ev) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream2 && h->stream2 != h->stream) cudaStreamDestroy(h->stream2);
     delete h;
 }
 
@@ -900,7 +950,7 @@ int tk_compress(tk_handle* h, int32_t k) {
     TK_TRY(upload_schedule(h));
     TK_TRY(alloc_work(h));
     TK_TRY(enqueue_compress(h, k));
-    TK_CUDA(cudaStreamSynchronize(h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream2));
     return 0;
 }
 
@@ -908,7 +958,7 @@ int tk_residual(tk_handle* h, int32_t k, double tol, double* out8) {
     if (!h || !h->begun || h->last_k != k) return set_error(TK_ESTATE, "call tk_compress(k) first");
     TK_CUDA(cudaSetDevice(h->device));
     TK_TRY(enqueue_residual(h, k, tol));
-    TK_CUDA(cudaStreamSynchronize(h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream2));
     if (out8) TK_CUDA(cudaMemcpy(out8, h->detail_d.p + (size_t)k * 8, 64, cudaMemcpyDeviceToHost));
     return 0;
 }
@@ -922,6 +972,9 @@ int tk_solve(tk_handle* h, double tol, int32_t* status, int64_t* niter, int32_t*
     if (!h->ev_solve[0]) { TK_CUDA(cudaEventCreate(&h->ev_solve[0])); TK_CUDA(cudaEventCreate(&h->ev_solve[1])); }
     TK_CUDA(cudaEventRecord(h->ev_solve[0], h->stream));
     TK_TRY(begin_solve(h));
+    // Two streams: `stream` advances the Krylov bases (iteration k+1 needs nothing from the compressed solve of
+    // iteration k), `stream2` runs eigensolve -> CP assembly -> residual for iteration k as soon as step k is
+    // done.  The host polls the device status word LAG iterations behind, so it never stalls the GPU queue.
     const int LAG = 3, RING = 8;
     int st = ST_RUNNING;
     for (int k = 2; k <= h->nmax; ++k) {
@@ -931,14 +984,20 @@ int tk_solve(tk_handle* h, double tol, int32_t* status, int64_t* niter, int32_t*
             if (h->status_ring[slot] != ST_RUNNING) break;
         }
         TK_TRY(enqueue_step_bases(h, k));
+        const int slot = k % RING;
+        TK_CUDA(cudaEventRecord(h->step_ev[slot], h->stream));
+        TK_CUDA(cudaStreamWaitEvent(h->stream2, h->step_ev[slot], 0));
         TK_TRY(enqueue_compress(h, k));
         TK_TRY(enqueue_residual(h, k, tol));
-        const int slot = k % RING;
-        TK_CUDA(cudaMemcpyAsync(&h->status_ring[slot], h->status_d.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        TK_CUDA(cudaEventRecord(h->ring_ev[slot], h->stream));
+        TK_CUDA(cudaMemcpyAsync(&h->status_ring[slot], h->status_d.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream2));
+        TK_CUDA(cudaEventRecord(h->ring_ev[slot], h->stream2));
     }
+    // join: the solve window ends when both streams have drained
+    TK_CUDA(cudaEventRecord(h->step_ev[0], h->stream2));
+    TK_CUDA(cudaStreamWaitEvent(h->stream, h->step_ev[0], 0));
     TK_CUDA(cudaEventRecord(h->ev_solve[1], h->stream));
     TK_CUDA(cudaStreamSynchronize(h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream2));
     int tk_ = 0, eigfail = 0;
     long long nit = 0;
     TK_CUDA(cudaMemcpy(&st, h->status_d.p, sizeof(int), cudaMemcpyDeviceToHost));

@@ -11,36 +11,37 @@
 namespace tk {
 
 // ------------------------------------------------------------------------------------------
-// Kernel (2): symmetric tridiagonal eigensolver, one CTA per problem, implicit-shift QL with
-// Wilkinson shifts.  The scalar recurrence that generates the Givens rotations is run
-// redundantly by every warp on a private copy of (d, e) in shared memory, so no block barrier
-// is ever needed; thread r owns row r of Q and applies each rotation to its own row as it is
-// generated, carrying the shared column in a register.  Q lives in shared memory when
-// k*ldz*8 fits, else directly in the global output.
+// Kernel (2): symmetric tridiagonal eigensolver, implicit-shift QL with Wilkinson shifts.
+// grid = (problems, row blocks).  The scalar recurrence that generates the Givens rotations is run
+// redundantly by every warp on a private copy of (d, e) in shared memory, so no barrier of any kind is
+// needed: a CTA owns `rows_per_blk` rows of Q (shared memory, one row per thread) and applies each
+// rotation to its rows as it is generated, carrying the shared column in a register.  Row blocks of
+// one problem never talk to each other.  The loads of the next (d, e) pair are issued one rotation
+// ahead and 1/sqrt replaces sqrt + division on the dependent chain.
 // in : T[prob*tstride + i] = diagonal, T[prob*tstride + ncol + i] = sub-diagonal (H[i+2,i+1])
 // out: theta[prob*thstride + i], Q[prob*qstride + i*ldq + r] = component r of eigenvector i
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) tridiag_eig_kernel(const double* __restrict__ T, long long tstride, int ncol,
-                                                           int k, double* theta, int thstride, double* Q,
-                                                           long long qstride, int ldq, int q_in_smem,
-                                                           const int* status, int* fail) {
+__global__ void __launch_bounds__(256) tridiag_eig_kernel(const double* __restrict__ T, long long tstride, int ncol,
+                                                          int k, int rows_per_blk, int ldz, double* theta, int thstride,
+                                                          double* Q, long long qstride, int ldq, const int* status,
+                                                          int* fail) {
     if (status && *status != ST_RUNNING) return;
     extern __shared__ double smem[];
     const int prob = blockIdx.x;
-    const int row = threadIdx.x, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    double* d = smem + (long long)warp * 2 * k;
+    const int row0 = blockIdx.y * rows_per_blk;
+    const int nrows = min(rows_per_blk, k - row0);
+    const int lrow = threadIdx.x, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5, lane = threadIdx.x & 31;
+    double* d = smem + (size_t)warp * 2 * k;
     double* e = d + k;
-    const int ldz = q_in_smem ? (k | 1) : ldq;   // odd stride: conflict-free column walks are not needed, rows are
-    double* Z = q_in_smem ? smem + (long long)nwarp * 2 * k : Q + (long long)prob * qstride;
+    double* Z = smem + (size_t)nwarp * 2 * k;          // Z[i*ldz + lrow]
     const double* Td = T + (long long)prob * tstride;
-    const int lane = threadIdx.x & 31;
     for (int i = lane; i < k; i += 32) {
         d[i] = Td[i];
         e[i] = (i < k - 1) ? Td[ncol + i] : 0.0;
     }
-    const bool active = row < k;
+    const bool active = lrow < nrows;
     if (active)
-        for (int i = 0; i < k; ++i) Z[(long long)i * ldz + row] = (i == row) ? 1.0 : 0.0;
+        for (int i = 0; i < k; ++i) Z[(size_t)i * ldz + lrow] = (i == row0 + lrow) ? 1.0 : 0.0;
     __syncwarp();
     const double EPS = 2.220446049250313e-16;
     bool failed = false;
@@ -59,34 +60,40 @@ __global__ void __launch_bounds__(1024) tridiag_eig_kernel(const double* __restr
             g = d[m] - d[l] + e[l] / (g + copysign(r, g));
             double s = 1.0, c = 1.0, pp = 0.0;
             int last = m;
-            double zc = active ? Z[(long long)m * ldz + row] : 0.0;
+            double zc = active ? Z[(size_t)m * ldz + lrow] : 0.0;
             bool underflow = false;
+            double e_i = e[m - 1], d_i = d[m - 1], d_ip1 = d[m];
             for (int i = m - 1; i >= l; --i) {
-                const double f = s * e[i], b = c * e[i];
-                r = sqrt(fma(f, f, g * g));
-                e[i + 1] = r;
-                if (r == 0.0) {
-                    d[i + 1] -= pp;
+                // operands of the NEXT rotation: never written during this sweep, so they can be fetched now
+                const double e_n = (i > l) ? e[i - 1] : 0.0, d_n = (i > l) ? d[i - 1] : 0.0;
+                const double zi = active ? Z[(size_t)i * ldz + lrow] : 0.0;
+                const double f = s * e_i, b = c * e_i;
+                const double h2 = fma(f, f, g * g);
+                if (h2 == 0.0) {
+                    e[i + 1] = 0.0;
+                    d[i + 1] = d_ip1 - pp;
                     e[m] = 0.0;
                     underflow = true;
                     break;
                 }
-                const double rinv = 1.0 / r;
+                const double rinv = rsqrt(h2);
+                r = h2 * rinv;
+                e[i + 1] = r;
                 s = f * rinv;
                 c = g * rinv;
-                g = d[i + 1] - pp;
-                r = fma(d[i] - g, s, 2.0 * c * b);
+                g = d_ip1 - pp;
+                r = fma(d_i - g, s, 2.0 * c * b);
                 pp = s * r;
                 d[i + 1] = g + pp;
                 g = fma(c, r, -b);
                 if (active) {
-                    const double zi = Z[(long long)i * ldz + row];
-                    Z[(long long)(i + 1) * ldz + row] = fma(s, zi, c * zc);
+                    Z[(size_t)(i + 1) * ldz + lrow] = fma(s, zi, c * zc);
                     zc = fma(c, zi, -s * zc);
                 }
                 last = i;
+                e_i = e_n; d_ip1 = d_i; d_i = d_n;
             }
-            if (active) Z[(long long)last * ldz + row] = zc;
+            if (active) Z[(size_t)last * ldz + lrow] = zc;
             if (underflow) continue;
             d[l] -= pp;
             e[l] = g;
@@ -95,11 +102,12 @@ __global__ void __launch_bounds__(1024) tridiag_eig_kernel(const double* __restr
         if (failed) break;
     }
     __syncwarp();
-    if (active) theta[(long long)prob * thstride + row] = d[row];
+    if (blockIdx.y == 0)
+        for (int i = threadIdx.x; i < k; i += blockDim.x) theta[(long long)prob * thstride + i] = d[i];
     if (failed && threadIdx.x == 0 && fail) atomicExch(fail, 1);
-    if (q_in_smem && active) {
-        double* Qg = Q + (long long)prob * qstride;
-        for (int i = 0; i < k; ++i) Qg[(long long)i * ldq + row] = Z[(long long)i * ldz + row];
+    if (active) {
+        double* Qg = Q + (long long)prob * qstride + row0 + lrow;
+        for (int i = 0; i < k; ++i) Qg[(long long)i * ldq] = Z[(size_t)i * ldz + lrow];
     }
 }
 

@@ -117,8 +117,13 @@ __global__ void __launch_bounds__(512) lanczos_ttr_kernel(KrylovParams p, int k)
 // grid = (column chunks, modes); a warp streams one column (16-byte loads, 8 in flight per lane)
 // against the new vector staged in shared memory.  HBM-bound: 8*n bytes per column.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gram_row_kernel(KrylovParams p, int ncols, int cols_per_cta, int mode_base,
-                                                       int w_in_smem) {
+constexpr int GRAM_PSTRIDE = 16;   // partial sums per column (>= warps per column)
+
+template <int U, int THREADS>   // U = 16-byte loads in flight per lane and column (two columns are streamed at once)
+__global__ void __launch_bounds__(THREADS) gram_row_kernel(KrylovParams p, int ncols, int cols_per_cta, int mode_base,
+                                                       int w_in_smem, int wpc) {
+    // wpc = warps that share one column: every column is cut into wpc contiguous segments so all warps of the
+    // CTA stream equal amounts, whatever the number of columns.
     if (*p.status != ST_RUNNING) return;
     extern __shared__ double smem[];
     const int s = mode_base + blockIdx.y, n = p.n;
@@ -126,46 +131,74 @@ __global__ void __launch_bounds__(256) gram_row_kernel(KrylovParams p, int ncols
     const double* Vs = p.V + (long long)s * p.vstride;
     const double* wg = Vs + (long long)(ncols - 1) * p.ldv;
     const int nq = n >> 1;
+    double* part = smem;                                  // [cols_per_cta][GRAM_PSTRIDE] partial sums
+    double* wsm = smem + (size_t)cols_per_cta * GRAM_PSTRIDE;
     if (w_in_smem) {
-        const double2* w2 = reinterpret_cast<const double2*>(wg);
-        double2* s2 = reinterpret_cast<double2*>(smem);
-        for (int q = threadIdx.x; q < nq; q += blockDim.x) s2[q] = w2[q];
-        if ((n & 1) && threadIdx.x == 0) smem[n - 1] = wg[n - 1];
+        const double2* w2g = reinterpret_cast<const double2*>(wg);
+        double2* s2 = reinterpret_cast<double2*>(wsm);
+        int q = threadIdx.x;
+        for (; q + 3 * (int)blockDim.x < nq; q += 4 * blockDim.x) {
+            const double2 t0 = w2g[q], t1 = w2g[q + blockDim.x], t2 = w2g[q + 2 * blockDim.x], t3 = w2g[q + 3 * blockDim.x];
+            s2[q] = t0; s2[q + blockDim.x] = t1; s2[q + 2 * blockDim.x] = t2; s2[q + 3 * blockDim.x] = t3;
+        }
+        for (; q < nq; q += blockDim.x) s2[q] = w2g[q];
+        if ((n & 1) && threadIdx.x == 0) wsm[n - 1] = wg[n - 1];
         __syncthreads();
     }
-    const double* w = w_in_smem ? smem : wg;
+    const double* w = w_in_smem ? wsm : wg;
     const double2* w2 = reinterpret_cast<const double2*>(w);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    double* g = p.g + (long long)s * p.ncol;
-    for (int j = c0 + warp; j < c1; j += nwarp) {
-        const double* col = Vs + (long long)j * p.ldv;
-        const double2* c2 = reinterpret_cast<const double2*>(col);
-        double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0;
-        int q = lane;
-        for (; q + 224 < nq; q += 256) {
-            const double2 x0 = ld_stream2(c2 + q), x1 = ld_stream2(c2 + q + 32), x2 = ld_stream2(c2 + q + 64),
-                          x3 = ld_stream2(c2 + q + 96), x4 = ld_stream2(c2 + q + 128), x5 = ld_stream2(c2 + q + 160),
-                          x6 = ld_stream2(c2 + q + 192), x7 = ld_stream2(c2 + q + 224);
-            const double2 y0 = w2[q], y1 = w2[q + 32], y2 = w2[q + 64], y3 = w2[q + 96], y4 = w2[q + 128],
-                          y5 = w2[q + 160], y6 = w2[q + 192], y7 = w2[q + 224];
-            a0 = fma(x0.x, y0.x, a0); a0 = fma(x0.y, y0.y, a0);
-            a1 = fma(x1.x, y1.x, a1); a1 = fma(x1.y, y1.y, a1);
-            a2 = fma(x2.x, y2.x, a2); a2 = fma(x2.y, y2.y, a2);
-            a3 = fma(x3.x, y3.x, a3); a3 = fma(x3.y, y3.y, a3);
-            a4 = fma(x4.x, y4.x, a4); a4 = fma(x4.y, y4.y, a4);
-            a5 = fma(x5.x, y5.x, a5); a5 = fma(x5.y, y5.y, a5);
-            a6 = fma(x6.x, y6.x, a6); a6 = fma(x6.y, y6.y, a6);
-            a7 = fma(x7.x, y7.x, a7); a7 = fma(x7.y, y7.y, a7);
+    const int seg = warp % wpc, group = warp / wpc, ngroups = nwarp / wpc;
+    const int seglen = (((nq + wpc - 1) / wpc) + 31) & ~31;
+    const int q0 = seg * seglen, q1 = min(nq, q0 + seglen);
+    for (int j = c0 + group; j < c1; j += 2 * ngroups) {
+        const int jb = j + ngroups;
+        const bool two = jb < c1;
+        const double2* ca = reinterpret_cast<const double2*>(Vs + (long long)j * p.ldv);
+        const double2* cb = reinterpret_cast<const double2*>(Vs + (long long)(two ? jb : j) * p.ldv);
+        double a[U], b[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { a[u] = 0.0; b[u] = 0.0; }
+        int q = q0 + lane;
+        for (; q + 32 * (U - 1) < q1; q += 32 * U) {
+            double2 x[U], z[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) x[u] = ld_stream2(ca + q + 32 * u);
+#pragma unroll
+            for (int u = 0; u < U; ++u) z[u] = ld_stream2(cb + q + 32 * u);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double2 y = w2[q + 32 * u];
+                a[u] = fma(x[u].x, y.x, a[u]); a[u] = fma(x[u].y, y.y, a[u]);
+                b[u] = fma(z[u].x, y.x, b[u]); b[u] = fma(z[u].y, y.y, b[u]);
+            }
         }
-        for (; q < nq; q += 32) {
-            const double2 x0 = ld_stream2(c2 + q);
+        for (; q < q1; q += 32) {
+            const double2 x0 = ld_stream2(ca + q), z0 = ld_stream2(cb + q);
             const double2 y0 = w2[q];
-            a0 = fma(x0.x, y0.x, a0); a0 = fma(x0.y, y0.y, a0);
+            a[0] = fma(x0.x, y0.x, a[0]); a[0] = fma(x0.y, y0.y, a[0]);
+            b[0] = fma(z0.x, y0.x, b[0]); b[0] = fma(z0.y, y0.y, b[0]);
         }
-        if ((n & 1) && lane == 0) a0 = fma(col[n - 1], w[n - 1], a0);
-        double acc = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-        acc = warp_sum(acc);
-        if (lane == 0) g[j] = acc;
+        if ((n & 1) && seg == wpc - 1 && lane == 0) {
+            a[0] = fma(Vs[(long long)j * p.ldv + n - 1], w[n - 1], a[0]);
+            if (two) b[0] = fma(Vs[(long long)jb * p.ldv + n - 1], w[n - 1], b[0]);
+        }
+        double sa = 0.0, sb = 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) { sa += a[u]; sb += b[u]; }
+        sa = warp_sum(sa);
+        sb = warp_sum(sb);
+        if (lane == 0) {
+            part[(j - c0) * GRAM_PSTRIDE + seg] = sa;
+            if (two) part[(jb - c0) * GRAM_PSTRIDE + seg] = sb;
+        }
+    }
+    __syncthreads();
+    double* g = p.g + (long long)s * p.ncol;
+    for (int j = c0 + threadIdx.x; j < c1; j += blockDim.x) {
+        double acc = 0.0;
+        for (int sgi = 0; sgi < wpc; ++sgi) acc += part[(j - c0) * GRAM_PSTRIDE + sgi];
+        g[j] = acc;
     }
 }
 
