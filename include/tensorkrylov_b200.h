@@ -96,6 +96,10 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
 void tk_destroy(tk_handle* h);
 /* the modes [first, first+count) this rank owns */
 int tk_local_modes(const tk_handle* h, int32_t* first, int32_t* count);
+/* needed = 1 if this rank wants the operator and right-hand side of global mode s: its own modes, plus mode 0
+ * under TK_FLAG_REFERENCE_H1 (every rank advances its own copy of mode 1's Krylov recurrence instead of
+ * receiving H_1 over the wire).  Feeding modes a rank does not need is allowed and ignored. */
+int tk_needs_mode(const tk_handle* h, int32_t s, int32_t* needed);
 
 /* ---- inputs (global mode index s; calls for modes another rank owns are ignored) */
 /* KroneckerMatrix.M[s] as SparseMatrixCSC (tensor_struct.jl:168-212) */

@@ -205,7 +205,12 @@ class Solver:
         f, c = C.c_int32(), C.c_int32()
         check(lib.tk_local_modes(self.h, C.byref(f), C.byref(c)))
         self.first, self.count = f.value, c.value
-        self._keep = []
+        # global modes whose inputs this rank wants (its own, plus mode 0 under TK_FLAG_REFERENCE_H1)
+        self.fed = list(range(self.first, self.first + self.count))
+        need0 = C.c_int32()
+        check(lib.tk_needs_mode(self.h, 0, C.byref(need0)))
+        if need0.value and 0 not in self.fed:
+            self.fed.insert(0, 0)
 
     def close(self):
         if getattr(self, "h", None):
@@ -221,7 +226,7 @@ class Solver:
     # inputs
     def set_operators(self, M):
         seen = {}
-        for s in range(self.first, self.first + self.count):
+        for s in self.fed:
             A = M[s]
             if id(A) in seen:
                 check(lib.tk_share_operator(self.h, s, seen[id(A)]))
@@ -241,12 +246,12 @@ class Solver:
             seen[id(A)] = s
 
     def set_rhs(self, b):
-        first = b[self.first] if self.count else None
-        if self.count and all(bs is first for bs in b[self.first:self.first + self.count]):
+        first = b[self.fed[0]] if self.fed else None
+        if self.fed and all(b[s] is first for s in self.fed):
             v = _capi.as_f64(first)
             check(lib.tk_set_rhs_all(self.h, dptr(v), len(v)))
             return
-        for s in range(self.first, self.first + self.count):
+        for s in self.fed:
             v = _capi.as_f64(b[s])
             check(lib.tk_set_rhs(self.h, s, dptr(v), len(v)))
 

@@ -150,17 +150,22 @@ using namespace tk;
 
 struct tk_handle {
     int d = 0, dl = 0, first = 0, nmax = 0, ncol = 0, n = 0;
+    int dk = 0;          // modes the Krylov kernels advance: dl, plus a shadow copy of global mode 0 (slot dl) when the
+                         // reference's H_1-for-all-modes rule is on and another rank owns mode 0
+    int eig_slot = 0;    // local slot whose T feeds class 0 under TK_FLAG_REFERENCE_H1
     int instance = 0, matrixclass = 0, variant = 0, flags = 0, device = 0, rank = 0, world = 1;
     long long ldv = 0;
     int per_mode = 0, ncls = 1;
     int chunk_modes = 16, nchunks = 1, chunk_base = 0;
     cudaStream_t stream = nullptr;    // Krylov-step kernels (1)
-    cudaStream_t stream2 = nullptr;   // compressed solve + residual (2)-(4): runs one iteration behind, concurrently
+    cudaStream_t stream2 = nullptr;   // CP assembly + residual (3)(4): runs behind the Krylov steps, concurrently
+    cudaStream_t stream3 = nullptr;   // eigensolver (2): eig(k) overlaps Krylov step k+1 and assembly of k-1
+    std::vector<cudaEvent_t> eig_ev, asm_ev;
     std::vector<cudaEvent_t> step_ev;  // step k done on `stream` -> `stream2` may start iteration k
     ncclComm_t comm = nullptr;
 
     // Krylov state
-    DevBuf<double> V, b, T, Hd, bt, g, S, orthS, bnorm2, vscratch, Tq;
+    DevBuf<double> V, b, T, Hd, bt, g, S, orthS, bnorm2, vscratch;
     DevBuf<int> fallbacks, mode_op_d, status_d, term_k_d, eigfail_d;
     DevBuf<long long> niter_d;
     DevBuf<OpDesc> ops_d;
@@ -224,6 +229,14 @@ static int check_mode(const tk_handle* h, int s, bool* local) {
     return 0;
 }
 
+// local slots that hold global mode s: its own slot, and the shadow slot for mode 0
+static int slots_of(const tk_handle* h, int s, int out[2]) {
+    int n = 0;
+    if (s >= h->first && s < h->first + h->dl) out[n++] = s - h->first;
+    if (s == 0 && h->dk > h->dl) out[n++] = h->dl;
+    return n;
+}
+
 static cudaEvent_t next_event(tk_handle* h) {
     if (h->ev_used == h->ev_pool.size()) {
         cudaEvent_t e;
@@ -246,8 +259,8 @@ struct TimedScope {
 
 static int upload_ops(tk_handle* h) {
     if (!h->ops_dirty) return 0;
-    for (int s = 0; s < h->dl; ++s)
-        if (h->mode_op[s] < 0) return set_error(TK_ESTATE, "operator of mode %d not set", h->first + s);
+    for (int s = 0; s < h->dk; ++s)
+        if (h->mode_op[s] < 0) return set_error(TK_ESTATE, "operator of mode %d not set", s < h->dl ? h->first + s : 0);
     std::vector<OpDesc> descs(h->ops.size());
     for (size_t i = 0; i < h->ops.size(); ++i) {
         const HostOp& o = *h->ops[i];
@@ -262,7 +275,7 @@ static int upload_ops(tk_handle* h) {
     }
     TK_TRY(h->ops_d.alloc(std::max<size_t>(descs.size(), 1), false));
     TK_CUDA(cudaMemcpy(h->ops_d.p, descs.data(), descs.size() * sizeof(OpDesc), cudaMemcpyHostToDevice));
-    TK_CUDA(cudaMemcpy(h->mode_op_d.p, h->mode_op.data(), h->dl * sizeof(int), cudaMemcpyHostToDevice));
+    TK_CUDA(cudaMemcpy(h->mode_op_d.p, h->mode_op.data(), h->dk * sizeof(int), cudaMemcpyHostToDevice));
     h->ops_dirty = false;
     return 0;
 }
@@ -289,8 +302,8 @@ static int alloc_work(tk_handle* h) {
     const int kmax = h->nmax, tmax = std::max(h->tmax, 1);
     const int tld = (tmax + 3) & ~3;
     h->ldq = (h->ncol + 1) & ~1;
-    TK_TRY(h->theta.alloc((size_t)h->ncls * h->ncol));
-    TK_TRY(h->Q.alloc((size_t)h->ncls * h->ldq * h->ldq));
+    TK_TRY(h->theta.alloc(2 * (size_t)h->ncls * h->ncol));            // double-buffered: eig(k+1) overlaps assembly(k)
+    TK_TRY(h->Q.alloc(2 * (size_t)h->ncls * h->ldq * h->ldq));
     h->ystride = (long long)kmax * tld;
     TK_TRY(h->Y.alloc((size_t)h->dl * h->ystride));
     TK_TRY(h->Z.alloc((size_t)h->dl * h->ystride));
@@ -318,15 +331,15 @@ static int allow_smem(K kernel, size_t bytes) {
 // --- kernel (1) launches -------------------------------------------------------------------
 static double op_bytes_per_row(const tk_handle* h) {
     double acc = 0.0;
-    for (int s = 0; s < h->dl; ++s) acc += h->ops[h->mode_op[s]]->bytes_per_row();
-    return h->dl ? acc / h->dl : 0.0;
+    for (int s = 0; s < h->dk; ++s) acc += h->ops[h->mode_op[s]]->bytes_per_row();
+    return h->dk ? acc / h->dk : 0.0;
 }
 
 template <int CPM>
 static int launch_ttr_t(tk_handle* h, int k, int threads, size_t smem) {
     TK_TRY(allow_smem(lanczos_ttr_kernel<CPM>, smem));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(h->dl * CPM);
+    cfg.gridDim = dim3(h->dk * CPM);
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = h->stream;
@@ -342,14 +355,14 @@ static int launch_ttr_t(tk_handle* h, int k, int threads, size_t smem) {
 }
 
 static int launch_ttr(tk_handle* h, int k) {
-    const double bytes = (op_bytes_per_row(h) + 32.0) * (double)h->n * h->dl;
+    const double bytes = (op_bytes_per_row(h) + 32.0) * (double)h->n * h->dk;
     TimedScope ts(h, TM_TTR, bytes, h->stream);
     // CTAs per mode (one cluster): at least 2 whenever a slice keeps >= 2048 rows (measured best on B200 at
     // n = 10^4), more when the modes alone cannot fill the machine or a slice would not fit in shared memory
     int cpm = 1;
     while (cpm < 8 && ((size_t)h->n * 8 / cpm > smem_limit(h) ||
                        (h->n / (2 * cpm) >= 2048 && cpm < 2) ||
-                       (h->n / (2 * cpm) >= 512 && (long long)h->dl * cpm < 296)))
+                       (h->n / (2 * cpm) >= 512 && (long long)h->dk * cpm < 296)))
         cpm *= 2;
     if (env_int("TK_TTR_CPM", 0)) cpm = env_int("TK_TTR_CPM", 0);
     const int chunk = (((h->n + cpm - 1) / cpm) + 1) & ~1;
@@ -409,7 +422,7 @@ static int mgs_smem(tk_handle* h, size_t* smem, double** vscr) {
     if (need <= smem_limit(h)) {
         *smem = need; *vscr = nullptr;
     } else {
-        if (!h->vscratch.p) TK_TRY(h->vscratch.alloc((size_t)h->dl * h->ldv));
+        if (!h->vscratch.p) TK_TRY(h->vscratch.alloc((size_t)h->dk * h->ldv));
         *smem = (size_t)h->ncol * 8; *vscr = h->vscratch.p;
     }
     return 0;
@@ -431,9 +444,9 @@ static int launch_arnoldi(tk_handle* h, int k) {
     size_t smem; double* vscr;
     TK_TRY(mgs_smem(h, &smem, &vscr));
     TK_TRY(allow_smem(arnoldi_mgs_kernel, smem));
-    const double bytes = (16.0 * k + op_bytes_per_row(h) + 24.0) * (double)h->n * h->dl;
+    const double bytes = (16.0 * k + op_bytes_per_row(h) + 24.0) * (double)h->n * h->dk;
     TimedScope ts(h, TM_MGS, bytes, h->stream);
-    arnoldi_mgs_kernel<<<h->dl, 512, smem, h->stream>>>(h->kp(), k, vscr);
+    arnoldi_mgs_kernel<<<h->dk, 512, smem, h->stream>>>(h->kp(), k, vscr);
     h->launches++;
     TK_CUDA(cudaGetLastError());
     return 0;
@@ -449,8 +462,8 @@ static int enqueue_step_bases(tk_handle* h, int k) {
     } else {
         TK_TRY(launch_ttr(h, k));
         if (h->variant == TK_LANCZOS_REORTH) {
-            TK_TRY(launch_gram(h, k + 1, 0, h->dl));
-            TK_TRY(launch_monitor(h, k, 0, h->dl, 1));
+            TK_TRY(launch_gram(h, k + 1, 0, h->dk));
+            TK_TRY(launch_monitor(h, k, 0, h->dk, 1));
         } else {
             TK_TRY(launch_gram(h, k + 1, 0, mode0));
             TK_TRY(launch_monitor(h, k, 0, mode0, 0));
@@ -488,8 +501,8 @@ static CompressParams make_cp(tk_handle* h, int k) {
     CompressParams c;
     c.k = k; c.t = se.t; c.tld = (se.t + 3) & ~3; c.ncol = h->ncol;
     c.per_mode = h->per_mode;
-    c.theta = h->theta.p; c.thstride = h->ncol;
-    c.Q = h->Q.p; c.qstride = (long long)h->ldq * h->ldq; c.ldq = h->ldq;
+    c.theta = h->theta.p + (size_t)(k & 1) * h->ncls * h->ncol; c.thstride = h->ncol;
+    c.Q = h->Q.p + (size_t)(k & 1) * h->ncls * h->ldq * h->ldq; c.qstride = (long long)h->ldq * h->ldq; c.ldq = h->ldq;
     c.bt = h->bt.p;
     c.alpha = h->alpha_d.p + se.off; c.omega = h->omega_d.p + se.off;
     c.lam_inv = 1.0 / se.lambda_min;
@@ -501,27 +514,26 @@ static CompressParams make_cp(tk_handle* h, int k) {
     return c;
 }
 
-// solve_compressed_system (tensor_krylov_method.jl:10-34)
-static int enqueue_compress(tk_handle* h, int k) {
+// solve_compressed_system (tensor_krylov_method.jl:10-34), first half: the eigendecomposition(s)
+static int enqueue_eig(tk_handle* h, int k) {
     if (h->instance == TK_NONSYM)
         return set_error(TK_EUNSUPPORTED, "NonSymInstance compressed solve (Hessenberg exponential) is not implemented yet");
-    const double* Tsrc = h->T.p;
-    long long tstride = 3LL * h->ncol;
-    if (!h->per_mode && h->world > 1) {
-        // the reference exponentiates H_1 for every mode: ship mode 1's tridiagonal to all ranks
-        TK_NCCL(g_nccl.Broadcast(h->T.p, h->Tq.p, 3 * (size_t)h->ncol, ncclDouble, 0, h->comm, h->stream2));
-        Tsrc = h->Tq.p;
-    }
-    {
-        TimedScope ts(h, TM_EIG, 0.0, h->stream2);
-        TK_TRY(launch_eig(Tsrc, tstride, h->ncol, k, h->ncls, h->theta.p, h->ncol, h->Q.p, (long long)h->ldq * h->ldq,
-                          h->ldq, h->status_d.p, h->eigfail_d.p, h->stream2));
-        h->launches++;
-    }
+    // under TK_FLAG_REFERENCE_H1 the one problem is mode 1's H (this rank's own copy or its shadow copy)
+    const double* Tsrc = h->per_mode ? h->T.p : h->T.p + (size_t)h->eig_slot * 3 * h->ncol;
+    CompressParams c = make_cp(h, k);
+    TimedScope ts(h, TM_EIG, 0.0, h->stream3);
+    TK_TRY(launch_eig(Tsrc, 3LL * h->ncol, h->ncol, k, h->ncls, const_cast<double*>(c.theta), h->ncol, const_cast<double*>(c.Q),
+                      c.qstride, h->ldq, h->status_d.p, h->eigfail_d.p, h->stream3));
+    h->launches++;
+    return 0;
+}
+
+// second half: CP assembly of Y_s for every local mode
+static int enqueue_assemble(tk_handle* h, int k) {
     CompressParams c = make_cp(h, k);
     const size_t smem = ((size_t)2 * k + (size_t)k * ASM_TJ) * 8;
     TK_TRY(allow_smem(assemble_cp_kernel, smem));
-    {
+    if (h->dl > 0) {
         TimedScope ts(h, TM_ASM, 0.0, h->stream2);
         assemble_cp_kernel<<<h->dl, 256, smem, h->stream2>>>(c);
         h->launches++;
@@ -534,7 +546,7 @@ static int enqueue_compress(tk_handle* h, int k) {
 // residualnorm! (utils.jl:402-443) + exits of the loop body (tensor_krylov_method.jl:85-118)
 static int enqueue_residual(tk_handle* h, int k, double tol) {
     CompressParams c = make_cp(h, k);
-    {
+    if (h->dl > 0) {
         TimedScope ts(h, TM_ASM, 0.0, h->stream2);
         gram_blocks_kernel<<<h->dl, 256, 0, h->stream2>>>(c);
         h->launches++;
@@ -569,8 +581,8 @@ static int enqueue_residual(tk_handle* h, int k, double tol) {
 
 static int reset_state(tk_handle* h) {
     TK_TRY(upload_ops(h));
-    for (int s = 0; s < h->dl; ++s)
-        if (!h->rhs_set[s]) return set_error(TK_ESTATE, "right-hand side of mode %d not set", h->first + s);
+    for (int s = 0; s < h->dk; ++s)
+        if (!h->rhs_set[s]) return set_error(TK_ESTATE, "right-hand side of mode %d not set", s < h->dl ? h->first + s : 0);
     const int run = ST_RUNNING, zero = 0;
     const long long nit = h->nmax;
     TK_CUDA(cudaMemcpyAsync(h->status_d.p, &run, sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -596,8 +608,8 @@ static int reset_state(tk_handle* h) {
 // orthonormalize!(decomp, b), initialize_compressed_rhs, kronprodnorm   (tensor_krylov_method.jl:48-55)
 static int begin_solve(tk_handle* h) {
     TK_TRY(reset_state(h));
-    if (h->dl > 0) {
-        init_basis_kernel<<<h->dl, 512, 0, h->stream>>>(h->kp(), h->bnorm2.p);
+    if (h->dk > 0) {
+        init_basis_kernel<<<h->dk, 512, 0, h->stream>>>(h->kp(), h->bnorm2.p);
         h->launches++;
         TK_CUDA(cudaGetLastError());
     }
@@ -623,7 +635,7 @@ static int begin_solve(tk_handle* h) {
     TK_CUDA(cudaStreamSynchronize(h->stream));
     // Gram "row" of column 1 starts the orthogonality bookkeeping, then step k = 1
     const int mode0 = (h->first == 0 && h->dl > 0) ? 1 : 0;
-    const int nmon = h->variant == TK_LANCZOS_REORTH ? h->dl : mode0;
+    const int nmon = h->variant == TK_LANCZOS_REORTH ? h->dk : mode0;
     TK_TRY(launch_gram(h, 1, 0, nmon));
     TK_TRY(launch_monitor(h, 0, 0, nmon, 0));
     TK_TRY(enqueue_step_bases(h, 1));
@@ -702,13 +714,21 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
     h->nchunks = std::max(1, (per + mc - 1) / mc + ((per % mc) && world > 1 ? 1 : 0));
     h->per_mode = (flags & TK_FLAG_REFERENCE_H1) ? 0 : 1;
     h->ncls = h->per_mode ? std::max(h->dl, 1) : 1;
+    const bool shadow = !h->per_mode && h->first != 0;   // every rank advances its own copy of mode 1: no broadcast needed
+    h->dk = h->dl + (shadow ? 1 : 0);
+    h->eig_slot = shadow ? h->dl : 0;
 
     TK_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     if (env_int("TK_SINGLE_STREAM", 0)) h->stream2 = h->stream;
     else TK_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    if (env_int("TK_SINGLE_STREAM", 0) || env_int("TK_TWO_STREAMS", 0)) h->stream3 = h->stream2;
+    else TK_CUDA(cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
+    h->eig_ev.resize(8); h->asm_ev.resize(8);
+    for (auto& e : h->eig_ev) TK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : h->asm_ev) TK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     h->step_ev.resize(8);
     for (auto& e : h->step_ev) TK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    const size_t dl = std::max(h->dl, 1);
+    const size_t dl = std::max(h->dk, 1);
     TK_TRY(h->V.alloc(dl * (size_t)h->ncol * h->ldv, false));
     TK_TRY(h->b.alloc(dl * (size_t)h->ldv));
     TK_TRY(h->T.alloc(dl * 3 * (size_t)h->ncol));
@@ -729,7 +749,6 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
     TK_TRY(h->projres_d.alloc(nmax));
     TK_TRY(h->orth_d.alloc(nmax));
     TK_TRY(h->detail_d.alloc((size_t)(nmax + 1) * 8));
-    TK_TRY(h->Tq.alloc(3 * (size_t)h->ncol));
     h->mode_op.assign(dl, -1);
     h->rhs_set.assign(dl, 0);
     h->sched.assign(nmax + 1, SchedEntry());
@@ -751,12 +770,16 @@ void tk_destroy(tk_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->stream2) cudaStreamSynchronize(h->stream2);
+    if (h->stream3) cudaStreamSynchronize(h->stream3);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     for (auto e : h->ev_solve) if (e) cudaEventDestroy(e);
     for (auto e : h->ring_ev) cudaEventDestroy(e);
     if (h->status_ring) cudaFreeHost(h->status_ring);
     for (auto e : h->step_ev) cudaEventDestroy(e);
+    for (auto e : h->eig_ev) cudaEventDestroy(e);
+    for (auto e : h->asm_ev) cudaEventDestroy(e);
+    if (h->stream3 && h->stream3 != h->stream2 && h->stream3 != h->stream) cudaStreamDestroy(h->stream3);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream2 && h->stream2 != h->stream) cudaStreamDestroy(h->stream2);
     delete h;
@@ -774,7 +797,9 @@ int tk_set_operator_csc(tk_handle* h, int32_t s, int64_t n, const int64_t* colpt
     TK_TRY(check_mode(h, s, &local));
     if (n != h->n) return set_error(TK_EINVAL, "operator order %lld != n = %d (system.jl:27-28)", (long long)n, h->n);
     if (!colptr || !rowval || !nzval) return set_error(TK_EINVAL, "null CSC array");
-    if (!local) return 0;
+    int slots[2];
+    const int nslots = slots_of(h, s, slots);
+    if (nslots == 0) return 0;
     TK_CUDA(cudaSetDevice(h->device));
     if (colptr[0] != 1) return set_error(TK_EINVAL, "colptr must be 1-based (Julia SparseMatrixCSC)");
     const int64_t nnz = colptr[n] - 1;
@@ -825,7 +850,7 @@ int tk_set_operator_csc(tk_handle* h, int32_t s, int64_t n, const int64_t* colpt
         TK_CUDA(cudaMemcpy(op->colidx.p, colidx.data(), 4 * colidx.size(), cudaMemcpyHostToDevice));
     }
     h->ops.push_back(std::move(op));
-    h->mode_op[s - h->first] = (int)h->ops.size() - 1;
+    for (int i = 0; i < nslots; ++i) h->mode_op[slots[i]] = (int)h->ops.size() - 1;
     h->ops_dirty = true;
     return 0;
 }
@@ -836,7 +861,9 @@ int tk_set_operator_dense(tk_handle* h, int32_t s, int64_t n, const double* a, c
     if (n != h->n) return set_error(TK_EINVAL, "operator order %lld != n = %d", (long long)n, h->n);
     if (!a) return set_error(TK_EINVAL, "null matrix");
     if (uplo != 'L' && uplo != 'F') return set_error(TK_EINVAL, "uplo must be 'L' or 'F'");
-    if (!local) return 0;
+    int slots[2];
+    const int nslots = slots_of(h, s, slots);
+    if (nslots == 0) return 0;
     TK_CUDA(cudaSetDevice(h->device));
     std::unique_ptr<HostOp> op(new HostOp());
     op->type = OP_DENSE; op->ld = n; op->nnz = n * n;
@@ -853,7 +880,7 @@ int tk_set_operator_dense(tk_handle* h, int32_t s, int64_t n, const double* a, c
         TK_CUDA(cudaMemcpy(op->vals.p, full.data(), 8 * full.size(), cudaMemcpyHostToDevice));
     }
     h->ops.push_back(std::move(op));
-    h->mode_op[s - h->first] = (int)h->ops.size() - 1;
+    for (int i = 0; i < nslots; ++i) h->mode_op[slots[i]] = (int)h->ops.size() - 1;
     h->ops_dirty = true;
     return 0;
 }
@@ -862,11 +889,22 @@ int tk_share_operator(tk_handle* h, int32_t s_dst, int32_t s_src) {
     bool ld = false, ls = false;
     TK_TRY(check_mode(h, s_dst, &ld));
     TK_TRY(check_mode(h, s_src, &ls));
-    if (!ld) return 0;
-    if (!ls) return set_error(TK_EINVAL, "mode %d is owned by another rank; set its operator on this rank first", s_src);
-    if (h->mode_op[s_src - h->first] < 0) return set_error(TK_ESTATE, "operator of mode %d not set", s_src);
-    h->mode_op[s_dst - h->first] = h->mode_op[s_src - h->first];
+    int dst[2], src[2];
+    const int nd = slots_of(h, s_dst, dst), ns = slots_of(h, s_src, src);
+    if (nd == 0) return 0;
+    if (ns == 0) return set_error(TK_EINVAL, "mode %d is not held by this rank; set its operator here first", s_src);
+    if (h->mode_op[src[0]] < 0) return set_error(TK_ESTATE, "operator of mode %d not set", s_src);
+    for (int i = 0; i < nd; ++i) h->mode_op[dst[i]] = h->mode_op[src[0]];
     h->ops_dirty = true;
+    return 0;
+}
+
+int tk_needs_mode(const tk_handle* h, int32_t s, int32_t* needed) {
+    bool local = false;
+    TK_TRY(check_mode(h, s, &local));
+    if (!needed) return set_error(TK_EINVAL, "null output");
+    int slots[2];
+    *needed = slots_of(h, s, slots) > 0 ? 1 : 0;
     return 0;
 }
 
@@ -875,11 +913,15 @@ int tk_set_rhs(tk_handle* h, int32_t s, const double* b, int64_t n) {
     TK_TRY(check_mode(h, s, &local));
     if (n != h->n) return set_error(TK_EINVAL, "rhs length %lld != n = %d (system.jl:28)", (long long)n, h->n);
     if (!b) return set_error(TK_EINVAL, "null rhs");
-    if (!local) return 0;
+    int slots[2];
+    const int nslots = slots_of(h, s, slots);
+    if (nslots == 0) return 0;
     TK_CUDA(cudaSetDevice(h->device));
-    TK_CUDA(cudaMemcpyAsync(h->b.p + (size_t)(s - h->first) * h->ldv, b, 8 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    for (int i = 0; i < nslots; ++i) {
+        TK_CUDA(cudaMemcpyAsync(h->b.p + (size_t)slots[i] * h->ldv, b, 8 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+        h->rhs_set[slots[i]] = 1;
+    }
     TK_CUDA(cudaStreamSynchronize(h->stream));
-    h->rhs_set[s - h->first] = 1;
     return 0;
 }
 
@@ -887,8 +929,15 @@ int tk_set_rhs_all(tk_handle* h, const double* b, int64_t n) {
     if (!h || !b) return set_error(TK_EINVAL, "null argument");
     if (n != h->n) return set_error(TK_EINVAL, "rhs length %lld != n = %d", (long long)n, h->n);
     TK_CUDA(cudaSetDevice(h->device));
-    for (int s = 0; s < h->dl; ++s)
-        TK_CUDA(cudaMemcpyAsync(h->b.p + (size_t)s * h->ldv, b, 8 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    if (h->dk > 0) {
+        // one host->device copy, then replicate on the device (a 2D copy with source pitch 0 is not allowed, so
+        // double the filled prefix until every slot is written)
+        TK_CUDA(cudaMemcpyAsync(h->b.p, b, 8 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+        for (int filled = 1; filled < h->dk; filled *= 2) {
+            const int cnt = std::min(filled, h->dk - filled);
+            TK_CUDA(cudaMemcpyAsync(h->b.p + (size_t)filled * h->ldv, h->b.p, 8 * (size_t)cnt * h->ldv, cudaMemcpyDeviceToDevice, h->stream));
+        }
+    }
     TK_CUDA(cudaStreamSynchronize(h->stream));
     std::fill(h->rhs_set.begin(), h->rhs_set.end(), 1);
     return 0;
@@ -949,7 +998,9 @@ int tk_compress(tk_handle* h, int32_t k) {
     TK_CUDA(cudaSetDevice(h->device));
     TK_TRY(upload_schedule(h));
     TK_TRY(alloc_work(h));
-    TK_TRY(enqueue_compress(h, k));
+    TK_TRY(enqueue_eig(h, k));
+    TK_CUDA(cudaStreamSynchronize(h->stream3));
+    TK_TRY(enqueue_assemble(h, k));
     TK_CUDA(cudaStreamSynchronize(h->stream2));
     return 0;
 }
@@ -986,8 +1037,15 @@ int tk_solve(tk_handle* h, double tol, int32_t* status, int64_t* niter, int32_t*
         TK_TRY(enqueue_step_bases(h, k));
         const int slot = k % RING;
         TK_CUDA(cudaEventRecord(h->step_ev[slot], h->stream));
-        TK_CUDA(cudaStreamWaitEvent(h->stream2, h->step_ev[slot], 0));
-        TK_TRY(enqueue_compress(h, k));
+        // eigensolver stream: needs step k; its (theta, Q) buffer k&1 was last read by the assembly of k-2
+        TK_CUDA(cudaStreamWaitEvent(h->stream3, h->step_ev[slot], 0));
+        if (k - 2 >= 2) TK_CUDA(cudaStreamWaitEvent(h->stream3, h->asm_ev[(k - 2) % RING], 0));
+        TK_TRY(enqueue_eig(h, k));
+        TK_CUDA(cudaEventRecord(h->eig_ev[slot], h->stream3));
+        // assembly + residual stream
+        TK_CUDA(cudaStreamWaitEvent(h->stream2, h->eig_ev[slot], 0));
+        TK_TRY(enqueue_assemble(h, k));
+        TK_CUDA(cudaEventRecord(h->asm_ev[slot], h->stream2));
         TK_TRY(enqueue_residual(h, k, tol));
         TK_CUDA(cudaMemcpyAsync(&h->status_ring[slot], h->status_d.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream2));
         TK_CUDA(cudaEventRecord(h->ring_ev[slot], h->stream2));
@@ -998,6 +1056,7 @@ int tk_solve(tk_handle* h, double tol, int32_t* status, int64_t* niter, int32_t*
     TK_CUDA(cudaEventRecord(h->ev_solve[1], h->stream));
     TK_CUDA(cudaStreamSynchronize(h->stream));
     TK_CUDA(cudaStreamSynchronize(h->stream2));
+    TK_CUDA(cudaStreamSynchronize(h->stream3));
     int tk_ = 0, eigfail = 0;
     long long nit = 0;
     TK_CUDA(cudaMemcpy(&st, h->status_d.p, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1129,10 +1188,11 @@ int tk_get_eig(tk_handle* h, int32_t s, int32_t k, double* theta, double* Q) {
     if (!local) return set_error(TK_EINVAL, "mode %d is owned by another rank", s);
     TK_CUDA(cudaSetDevice(h->device));
     const int cls = h->per_mode ? s - h->first : 0;
-    if (theta) TK_CUDA(cudaMemcpy(theta, h->theta.p + (size_t)cls * h->ncol, 8 * (size_t)k, cudaMemcpyDeviceToHost));
+    const size_t par = (size_t)(k & 1);
+    if (theta) TK_CUDA(cudaMemcpy(theta, h->theta.p + (par * h->ncls + cls) * h->ncol, 8 * (size_t)k, cudaMemcpyDeviceToHost));
     if (Q) {
         std::vector<double> q((size_t)h->ldq * k);
-        TK_CUDA(cudaMemcpy(q.data(), h->Q.p + (size_t)cls * h->ldq * h->ldq, 8 * q.size(), cudaMemcpyDeviceToHost));
+        TK_CUDA(cudaMemcpy(q.data(), h->Q.p + (par * h->ncls + cls) * h->ldq * h->ldq, 8 * q.size(), cudaMemcpyDeviceToHost));
         for (int i = 0; i < k; ++i)
             for (int r = 0; r < k; ++r) Q[(size_t)i * k + r] = q[(size_t)i * h->ldq + r];
     }
