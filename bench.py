@@ -161,6 +161,8 @@ def run_reference(a):
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 def run_b200(a):
+    # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/tk_nccl_%h_%p.log")
     import torch
     import torch.distributed as dist
     tk = entry.load_package()

@@ -94,6 +94,9 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
               int32_t matrixclass, int32_t variant, int32_t flags, int32_t device,
               int32_t rank, int32_t world, const void* unique_id);
 void tk_destroy(tk_handle* h);
+/* Destroyed handles leave their device blocks in a process-level cache so the next tk_create of the same shape
+ * costs no cudaMalloc (the reference allocates its whole state per call; so does a drop-in).  This frees the cache. */
+int tk_release_cache(void);
 /* the modes [first, first+count) this rank owns */
 int tk_local_modes(const tk_handle* h, int32_t* first, int32_t* count);
 /* needed = 1 if this rank wants the operator and right-hand side of global mode s: its own modes, plus mode 0

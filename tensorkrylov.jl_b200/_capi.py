@@ -26,7 +26,7 @@ TK_FLAG_REFERENCE_H1, TK_FLAG_FIXED_ITERATIONS, TK_FLAG_TIME_KERNELS, TK_FLAG_TI
 EXPORTS = [
     "tk_last_error", "tk_version", "tk_device_count",
     "tk_tables_load", "tk_tables_sym_lookup", "tk_nonsym_coefficients", "tk_laplace_extremes",
-    "tk_comm_unique_id", "tk_create", "tk_destroy", "tk_local_modes", "tk_needs_mode",
+    "tk_comm_unique_id", "tk_create", "tk_destroy", "tk_release_cache", "tk_local_modes", "tk_needs_mode",
     "tk_set_operator_csc", "tk_set_operator_dense", "tk_share_operator", "tk_set_rhs", "tk_set_rhs_all",
     "tk_set_schedule", "tk_schedule_laplace", "tk_solve", "tk_solution_rank", "tk_get_solution",
     "tk_begin", "tk_step_bases", "tk_compress", "tk_residual",
@@ -61,6 +61,7 @@ def _load():
         "tk_comm_unique_id": (C.c_int, [p]),
         "tk_create": (C.c_int, [C.POINTER(p), i32, pi64, i32, i32, i32, i32, i32, i32, i32, i32, p]),
         "tk_destroy": (None, [p]),
+        "tk_release_cache": (C.c_int, []),
         "tk_local_modes": (C.c_int, [p, pi32, pi32]),
         "tk_needs_mode": (C.c_int, [p, i32, pi32]),
         "tk_set_operator_csc": (C.c_int, [p, i32, i64, pi64, pi64, pd]),

@@ -23,6 +23,7 @@
 
 #include "../../include/tensorkrylov_b200.h"
 #include "tk_compress.cuh"
+#include "tk_expm.cuh"
 #include "tk_host.h"
 #include "tk_krylov.cuh"
 
@@ -84,6 +85,11 @@ static int nccl_bind() {
     return 0;
 }
 
+// One NCCL communicator per unique id and process, shared by every handle created with that id (a unique id
+// may initialise only one communicator; solves come and go, the communicator stays).
+struct CommEntry { ncclComm_t comm; int rank, world, refs; };
+static std::map<std::string, CommEntry> g_comms;
+
 #define TK_NCCL(call)                                                                              \
     do {                                                                                           \
         ncclResult_t r__ = (call);                                                                 \
@@ -91,22 +97,66 @@ static int nccl_bind() {
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
-// device buffer with RAII
+// Device memory: a process-level cache of freed blocks keyed by (device, bytes).  The reference's entry point
+// builds its whole state per call (decompositions.jl:127-174); a drop-in does the same, and cudaMalloc/cudaFree
+// of multi-GB bases would otherwise cost more than the solve.  tk_release_cache() returns everything.
 // ---------------------------------------------------------------------------------------------
+static std::map<std::pair<int, size_t>, std::vector<void*>> g_pool;
+static size_t g_pool_bytes = 0;
+
+static void pool_trim() {
+    for (auto& kv : g_pool) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(kv.first.first);
+        for (void* q : kv.second) cudaFree(q);
+        cudaSetDevice(cur);
+    }
+    g_pool.clear();
+    g_pool_bytes = 0;
+}
+
+static cudaError_t pool_alloc(void** out, size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto it = g_pool.find(std::make_pair(dev, bytes));
+    if (it != g_pool.end() && !it->second.empty()) {
+        *out = it->second.back();
+        it->second.pop_back();
+        g_pool_bytes -= bytes;
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        pool_trim();
+        e = cudaMalloc(out, bytes);
+    }
+    return e;
+}
+
+static void pool_free(void* q, size_t bytes) {
+    int dev = 0;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, q) == cudaSuccess) dev = attr.device; else cudaGetLastError();
+    g_pool[std::make_pair(dev, bytes)].push_back(q);
+    g_pool_bytes += bytes;
+}
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t count = 0;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) pool_free(p, count * sizeof(T));
         p = nullptr;
         count = 0;
     }
     int alloc(size_t n, bool zero = true) {
         release();
         if (n == 0) n = 1;
-        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        cudaError_t e = pool_alloc(reinterpret_cast<void**>(&p), n * sizeof(T));
         if (e != cudaSuccess) {
             p = nullptr;
             return set_error(TK_ENOMEM, "cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
@@ -128,6 +178,7 @@ struct HostOp {
     long long nnz = 0;
     DevBuf<double> vals;   // diag / val / dense
     DevBuf<int> rowptr, colidx;
+    double norm_bound = 0.0;   // sqrt(||A||_1 ||A||_inf) >= ||A||_2, bounds the squarings of the Hessenberg exponential
     double bytes_per_row() const {  // operator bytes streamed per row by one SpMV
         if (type == OP_DIA) return 8.0 * ndiag;
         if (type == OP_CSR) return ld > 0 ? (12.0 * nnz + 4.0 * (ld + 1)) / (double)ld : 0.0;
@@ -159,7 +210,10 @@ struct tk_handle {
     int chunk_modes = 16, nchunks = 1, chunk_base = 0;
     cudaStream_t stream = nullptr;    // Krylov-step kernels (1)
     cudaStream_t stream2 = nullptr;   // CP assembly + residual (3)(4): runs behind the Krylov steps, concurrently
-    cudaStream_t stream3 = nullptr;   // eigensolver (2): eig(k) overlaps Krylov step k+1 and assembly of k-1
+    // eigensolver (2): eig(k) only needs step k, so consecutive k run concurrently on NEIG round-robin streams
+    // (one SM each) and overlap the Krylov steps and the assembly of earlier iterations
+    static constexpr int NEIG = 4, NBUF = 8;
+    cudaStream_t stream3[NEIG] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> eig_ev, asm_ev;
     std::vector<cudaEvent_t> step_ev;  // step k done on `stream` -> `stream2` may start iteration k
     ncclComm_t comm = nullptr;
@@ -183,6 +237,9 @@ struct tk_handle {
 
     // compressed solve / residual
     DevBuf<double> theta, Q, Y, Z, E, bbm, partials, gathered, bnorm_d, relres_d, projres_d, orth_d, detail_d;
+    DevBuf<double> exW;                 // NonSymInstance: workspace of the batched matrix exponential
+    DevBuf<int> ex_nsq, ex_where, cls_mode_d;
+    int ex_ld = 0;
     int ldq = 0;
     long long ystride = 0, estride = 0, pstride_max = 0;
     bool work_ready = false;
@@ -302,8 +359,8 @@ static int alloc_work(tk_handle* h) {
     const int kmax = h->nmax, tmax = std::max(h->tmax, 1);
     const int tld = (tmax + 3) & ~3;
     h->ldq = (h->ncol + 1) & ~1;
-    TK_TRY(h->theta.alloc(2 * (size_t)h->ncls * h->ncol));            // double-buffered: eig(k+1) overlaps assembly(k)
-    TK_TRY(h->Q.alloc(2 * (size_t)h->ncls * h->ldq * h->ldq));
+    TK_TRY(h->theta.alloc(tk_handle::NBUF * (size_t)h->ncls * h->ncol));   // ring: eig(k+1..) overlap assembly(k)
+    TK_TRY(h->Q.alloc(tk_handle::NBUF * (size_t)h->ncls * h->ldq * h->ldq));
     h->ystride = (long long)kmax * tld;
     TK_TRY(h->Y.alloc((size_t)h->dl * h->ystride));
     TK_TRY(h->Z.alloc((size_t)h->dl * h->ystride));
@@ -313,6 +370,23 @@ static int alloc_work(tk_handle* h) {
     h->pstride_max = 5LL * tmax * tmax + 2LL * tmax + 8;
     TK_TRY(h->partials.alloc((size_t)h->nchunks * h->pstride_max));
     if (h->world > 1) TK_TRY(h->gathered.alloc((size_t)h->world * h->nchunks * h->pstride_max));
+    if (h->instance == TK_NONSYM) {
+        h->ex_ld = (h->nmax + 3) & ~3;
+        const size_t nmat = (size_t)h->ncls * tmax;
+        const size_t bytes = nmat * EX_SLOTS * (size_t)h->ex_ld * h->ex_ld * 8;
+        size_t free_b = 0, total_b = 0;
+        TK_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        if (bytes > free_b + g_pool_bytes)
+            return set_error(TK_ENOMEM, "matrix-exponential workspace needs %.1f GB (%zu matrices of order %d); use TK_FLAG_REFERENCE_H1 or fewer modes per GPU",
+                             bytes / 1e9, nmat, h->nmax);
+        TK_TRY(h->exW.alloc(nmat * EX_SLOTS * (size_t)h->ex_ld * h->ex_ld, false));
+        TK_TRY(h->ex_nsq.alloc(nmat));
+        TK_TRY(h->ex_where.alloc(nmat));
+        std::vector<int> cm(h->ncls);
+        for (int c = 0; c < h->ncls; ++c) cm[c] = h->per_mode ? c : h->eig_slot;
+        TK_TRY(h->cls_mode_d.alloc(h->ncls, false));
+        TK_CUDA(cudaMemcpy(h->cls_mode_d.p, cm.data(), sizeof(int) * cm.size(), cudaMemcpyHostToDevice));
+    }
     h->work_ready = true;
     return 0;
 }
@@ -501,8 +575,8 @@ static CompressParams make_cp(tk_handle* h, int k) {
     CompressParams c;
     c.k = k; c.t = se.t; c.tld = (se.t + 3) & ~3; c.ncol = h->ncol;
     c.per_mode = h->per_mode;
-    c.theta = h->theta.p + (size_t)(k & 1) * h->ncls * h->ncol; c.thstride = h->ncol;
-    c.Q = h->Q.p + (size_t)(k & 1) * h->ncls * h->ldq * h->ldq; c.qstride = (long long)h->ldq * h->ldq; c.ldq = h->ldq;
+    c.theta = h->theta.p + (size_t)(k % tk_handle::NBUF) * h->ncls * h->ncol; c.thstride = h->ncol;
+    c.Q = h->Q.p + (size_t)(k % tk_handle::NBUF) * h->ncls * h->ldq * h->ldq; c.qstride = (long long)h->ldq * h->ldq; c.ldq = h->ldq;
     c.bt = h->bt.p;
     c.alpha = h->alpha_d.p + se.off; c.omega = h->omega_d.p + se.off;
     c.lam_inv = 1.0 / se.lambda_min;
@@ -516,20 +590,74 @@ static CompressParams make_cp(tk_handle* h, int k) {
 
 // solve_compressed_system (tensor_krylov_method.jl:10-34), first half: the eigendecomposition(s)
 static int enqueue_eig(tk_handle* h, int k) {
-    if (h->instance == TK_NONSYM)
-        return set_error(TK_EUNSUPPORTED, "NonSymInstance compressed solve (Hessenberg exponential) is not implemented yet");
+    if (h->instance == TK_NONSYM) return 0;   // dense exponential instead, see enqueue_expm (runs on stream2)
     // under TK_FLAG_REFERENCE_H1 the one problem is mode 1's H (this rank's own copy or its shadow copy)
     const double* Tsrc = h->per_mode ? h->T.p : h->T.p + (size_t)h->eig_slot * 3 * h->ncol;
     CompressParams c = make_cp(h, k);
-    TimedScope ts(h, TM_EIG, 0.0, h->stream3);
+    cudaStream_t st = h->stream3[k % tk_handle::NEIG];
+    TimedScope ts(h, TM_EIG, 0.0, st);
     TK_TRY(launch_eig(Tsrc, 3LL * h->ncol, h->ncol, k, h->ncls, const_cast<double*>(c.theta), h->ncol, const_cast<double*>(c.Q),
-                      c.qstride, h->ldq, h->status_d.p, h->eigfail_d.p, h->stream3));
+                      c.qstride, h->ldq, h->status_d.p, h->eigfail_d.p, st));
     h->launches++;
+    return 0;
+}
+
+// NonSymInstance: Y_s[:,j] = exp(gamma_j H) b~_s through the batched Taylor scaling-and-squaring exponential
+static int enqueue_expm(tk_handle* h, int k) {
+    const SchedEntry& se = h->sched[k];
+    ExpmParams p;
+    p.k = k; p.ld = h->ex_ld; p.t = se.t; p.ncls = h->ncls; p.ncol = h->ncol;
+    p.mslot = (long long)h->ex_ld * h->ex_ld;
+    p.W = h->exW.p; p.nsq = h->ex_nsq.p; p.where = h->ex_where.p;
+    p.Hd = h->Hd.p; p.T = h->T.p; p.cls_mode = h->cls_mode_d.p;
+    p.alpha = h->alpha_d.p + se.off; p.lam_inv = 1.0 / se.lambda_min;
+    p.status = h->status_d.p;
+    const int nmat = h->ncls * se.t;
+    cudaStream_t st = h->stream2;
+    TimedScope ts(h, TM_EIG, 0.0, st);
+    expm_setup_kernel<<<nmat, 256, 0, st>>>(p);
+    h->launches++;
+    // upper bound on the squarings: ||gamma H||_1 <= |gamma| sqrt(k) ||H||_2 <= |gamma| sqrt(k) ||A||_2
+    double amax = 0.0, nb = 0.0;
+    for (int j = 0; j < se.t; ++j) amax = std::max(amax, std::fabs(h->alpha_pool[se.off + j]));
+    for (int s = 0; s < h->dk; ++s) nb = std::max(nb, h->ops[h->mode_op[s]]->norm_bound);
+    const double bound = amax * p.lam_inv * std::sqrt((double)k) * nb;
+    int smax = bound > EX_THETA ? (int)std::ceil(std::log2(bound / EX_THETA)) + 1 : 1;
+    smax = std::min(std::max(smax, 1), 60);
+    const int tiles = (k + 63) / 64;
+    dim3 grid(tiles, tiles, nmat);
+    auto gemm = [&](int a, int b, int c, int comb, double c0, double c1, double c2, double c3, double c4, int sq) {
+        GemmJob job; job.a = a; job.b = b; job.c = c; job.comb = comb; job.c0 = c0; job.c1 = c1; job.c2 = c2; job.c3 = c3;
+        job.c4 = c4; job.sq_step = sq;
+        expm_gemm_kernel<<<grid, 256, 0, st>>>(p, job);
+        h->launches++;
+    };
+    double f[17];
+    f[0] = 1.0;
+    for (int i = 1; i <= 16; ++i) f[i] = f[i - 1] / (double)i;    // 1/i!
+    gemm(0, 0, 1, 0, 0, 0, 0, 0, 0, -1);     // A2 = A A
+    gemm(1, 0, 2, 0, 0, 0, 0, 0, 0, -1);     // A3 = A2 A
+    gemm(1, 1, 3, 0, 0, 0, 0, 0, 0, -1);     // A4 = A2 A2
+    expm_top_kernel<<<dim3(std::max(1, (h->ex_ld * h->ex_ld + 255) / 256 / 4), nmat), 256, 0, st>>>(p, f[12], f[13], f[14], f[15], f[16]);
+    h->launches++;
+    gemm(3, 5, 4, 1, f[8], f[9], f[10], f[11], 0.0, -1);
+    gemm(3, 4, 5, 1, f[4], f[5], f[6], f[7], 0.0, -1);
+    gemm(3, 5, 4, 1, f[0], f[1], f[2], f[3], 0.0, -1);
+    for (int sq = 0; sq < smax; ++sq) gemm(0, 0, 0, 0, 0, 0, 0, 0, 0, sq);
+    TK_CUDA(cudaGetLastError());
+    const int tld = (se.t + 3) & ~3;
+    if (h->dl > 0) {
+        expm_apply_kernel<<<dim3(h->dl, se.t), 256, (size_t)k * 8, st>>>(p, h->per_mode, h->bt.p, h->Y.p, h->ystride, tld);
+        h->launches++;
+        TK_CUDA(cudaGetLastError());
+    }
+    h->last_k = k; h->last_t = se.t; h->last_tld = tld; h->last_lam_inv = p.lam_inv;
     return 0;
 }
 
 // second half: CP assembly of Y_s for every local mode
 static int enqueue_assemble(tk_handle* h, int k) {
+    if (h->instance == TK_NONSYM) return enqueue_expm(h, k);
     CompressParams c = make_cp(h, k);
     const size_t smem = ((size_t)2 * k + (size_t)k * ASM_TJ) * 8;
     TK_TRY(allow_smem(assemble_cp_kernel, smem));
@@ -721,8 +849,11 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
     TK_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     if (env_int("TK_SINGLE_STREAM", 0)) h->stream2 = h->stream;
     else TK_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
-    if (env_int("TK_SINGLE_STREAM", 0) || env_int("TK_TWO_STREAMS", 0)) h->stream3 = h->stream2;
-    else TK_CUDA(cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
+    for (int i = 0; i < tk_handle::NEIG; ++i) {
+        if (env_int("TK_SINGLE_STREAM", 0) || env_int("TK_TWO_STREAMS", 0)) h->stream3[i] = h->stream2;
+        else if (i >= env_int("TK_EIG_STREAMS", tk_handle::NEIG)) h->stream3[i] = h->stream3[0];
+        else TK_CUDA(cudaStreamCreateWithFlags(&h->stream3[i], cudaStreamNonBlocking));
+    }
     h->eig_ev.resize(8); h->asm_ev.resize(8);
     for (auto& e : h->eig_ev) TK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : h->asm_ev) TK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -757,9 +888,19 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
     for (auto& e : h->ring_ev) TK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     if (world > 1) {
         TK_TRY(nccl_bind());
-        ncclUniqueId id;
-        std::memcpy(&id, unique_id, 128);
-        TK_NCCL(g_nccl.CommInitRank(&h->comm, world, id, rank));
+        const std::string key(static_cast<const char*>(unique_id), 128);
+        auto it = g_comms.find(key);
+        if (it == g_comms.end()) {
+            ncclUniqueId id;
+            std::memcpy(&id, unique_id, 128);
+            ncclComm_t comm;
+            TK_NCCL(g_nccl.CommInitRank(&comm, world, id, rank));
+            it = g_comms.emplace(key, CommEntry{comm, rank, world, 0}).first;
+        } else if (it->second.rank != rank || it->second.world != world) {
+            return set_error(TK_EINVAL, "unique id already bound to rank %d of %d in this process", it->second.rank, it->second.world);
+        }
+        it->second.refs++;
+        h->comm = it->second.comm;
     }
     *out = h.release();
     return 0;
@@ -770,8 +911,7 @@ void tk_destroy(tk_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->stream2) cudaStreamSynchronize(h->stream2);
-    if (h->stream3) cudaStreamSynchronize(h->stream3);
-    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (auto st : h->stream3) if (st) cudaStreamSynchronize(st);
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     for (auto e : h->ev_solve) if (e) cudaEventDestroy(e);
     for (auto e : h->ring_ev) cudaEventDestroy(e);
@@ -779,10 +919,20 @@ void tk_destroy(tk_handle* h) {
     for (auto e : h->step_ev) cudaEventDestroy(e);
     for (auto e : h->eig_ev) cudaEventDestroy(e);
     for (auto e : h->asm_ev) cudaEventDestroy(e);
-    if (h->stream3 && h->stream3 != h->stream2 && h->stream3 != h->stream) cudaStreamDestroy(h->stream3);
+    for (int i = 0; i < tk_handle::NEIG; ++i) {
+        cudaStream_t st = h->stream3[i];
+        bool dup = (st == h->stream2 || st == h->stream || st == nullptr);
+        for (int j = 0; j < i; ++j) dup = dup || (h->stream3[j] == st);
+        if (!dup) cudaStreamDestroy(st);
+    }
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream2 && h->stream2 != h->stream) cudaStreamDestroy(h->stream2);
     delete h;
+}
+
+int tk_release_cache(void) {
+    pool_trim();
+    return 0;
 }
 
 int tk_local_modes(const tk_handle* h, int32_t* first, int32_t* count) {
@@ -814,6 +964,17 @@ int tk_set_operator_csc(tk_handle* h, int32_t s, int64_t n, const int64_t* colpt
     }
     std::unique_ptr<HostOp> op(new HostOp());
     op->ld = n; op->nnz = nnz;
+    {
+        std::vector<double> rows(n, 0.0);
+        double n1 = 0.0, ninf = 0.0;
+        for (int64_t j = 0; j < n; ++j) {
+            double cs = 0.0;
+            for (int64_t p = colptr[j] - 1; p < colptr[j + 1] - 1; ++p) { cs += std::fabs(nzval[p]); rows[rowval[p] - 1] += std::fabs(nzval[p]); }
+            n1 = std::max(n1, cs);
+        }
+        for (double r : rows) ninf = std::max(ninf, r);
+        op->norm_bound = std::sqrt(n1 * ninf);
+    }
     if (offs.size() <= (size_t)MAX_DIAG && !offs.empty()) {
         op->type = OP_DIA;
         op->ndiag = (int)offs.size();
@@ -867,6 +1028,21 @@ int tk_set_operator_dense(tk_handle* h, int32_t s, int64_t n, const double* a, c
     TK_CUDA(cudaSetDevice(h->device));
     std::unique_ptr<HostOp> op(new HostOp());
     op->type = OP_DENSE; op->ld = n; op->nnz = n * n;
+    {
+        std::vector<double> rows(n, 0.0);
+        double n1 = 0.0, ninf = 0.0;
+        for (int64_t j = 0; j < n; ++j) {
+            double cs = 0.0;
+            for (int64_t i = (uplo == 'L' ? j : 0); i < n; ++i) {
+                const double v = std::fabs(a[(size_t)j * n + i]);
+                cs += v; rows[i] += v;
+                if (uplo == 'L' && i != j) { rows[j] += v; }
+            }
+            n1 = std::max(n1, cs);
+        }
+        for (double r : rows) ninf = std::max(ninf, r);
+        op->norm_bound = uplo == 'L' ? ninf : std::sqrt(n1 * ninf);
+    }
     TK_TRY(op->vals.alloc((size_t)n * n, false));
     if (uplo == 'F') {
         TK_CUDA(cudaMemcpy(op->vals.p, a, 8 * (size_t)n * n, cudaMemcpyHostToDevice));
@@ -999,7 +1175,7 @@ int tk_compress(tk_handle* h, int32_t k) {
     TK_TRY(upload_schedule(h));
     TK_TRY(alloc_work(h));
     TK_TRY(enqueue_eig(h, k));
-    TK_CUDA(cudaStreamSynchronize(h->stream3));
+    TK_CUDA(cudaStreamSynchronize(h->stream3[k % tk_handle::NEIG]));
     TK_TRY(enqueue_assemble(h, k));
     TK_CUDA(cudaStreamSynchronize(h->stream2));
     return 0;
@@ -1026,7 +1202,7 @@ int tk_solve(tk_handle* h, double tol, int32_t* status, int64_t* niter, int32_t*
     // Two streams: `stream` advances the Krylov bases (iteration k+1 needs nothing from the compressed solve of
     // iteration k), `stream2` runs eigensolve -> CP assembly -> residual for iteration k as soon as step k is
     // done.  The host polls the device status word LAG iterations behind, so it never stalls the GPU queue.
-    const int LAG = 3, RING = 8;
+    const int LAG = 6, RING = 8;
     int st = ST_RUNNING;
     for (int k = 2; k <= h->nmax; ++k) {
         if (k - LAG >= 2) {
@@ -1038,10 +1214,11 @@ int tk_solve(tk_handle* h, double tol, int32_t* status, int64_t* niter, int32_t*
         const int slot = k % RING;
         TK_CUDA(cudaEventRecord(h->step_ev[slot], h->stream));
         // eigensolver stream: needs step k; its (theta, Q) buffer k&1 was last read by the assembly of k-2
-        TK_CUDA(cudaStreamWaitEvent(h->stream3, h->step_ev[slot], 0));
-        if (k - 2 >= 2) TK_CUDA(cudaStreamWaitEvent(h->stream3, h->asm_ev[(k - 2) % RING], 0));
+        cudaStream_t es = h->stream3[k % tk_handle::NEIG];
+        TK_CUDA(cudaStreamWaitEvent(es, h->step_ev[slot], 0));
+        if (k - tk_handle::NBUF >= 2) TK_CUDA(cudaStreamWaitEvent(es, h->asm_ev[(k - tk_handle::NBUF) % RING], 0));
         TK_TRY(enqueue_eig(h, k));
-        TK_CUDA(cudaEventRecord(h->eig_ev[slot], h->stream3));
+        TK_CUDA(cudaEventRecord(h->eig_ev[slot], es));
         // assembly + residual stream
         TK_CUDA(cudaStreamWaitEvent(h->stream2, h->eig_ev[slot], 0));
         TK_TRY(enqueue_assemble(h, k));
@@ -1056,7 +1233,7 @@ int tk_solve(tk_handle* h, double tol, int32_t* status, int64_t* niter, int32_t*
     TK_CUDA(cudaEventRecord(h->ev_solve[1], h->stream));
     TK_CUDA(cudaStreamSynchronize(h->stream));
     TK_CUDA(cudaStreamSynchronize(h->stream2));
-    TK_CUDA(cudaStreamSynchronize(h->stream3));
+    for (auto es : h->stream3) TK_CUDA(cudaStreamSynchronize(es));
     int tk_ = 0, eigfail = 0;
     long long nit = 0;
     TK_CUDA(cudaMemcpy(&st, h->status_d.p, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1188,7 +1365,7 @@ int tk_get_eig(tk_handle* h, int32_t s, int32_t k, double* theta, double* Q) {
     if (!local) return set_error(TK_EINVAL, "mode %d is owned by another rank", s);
     TK_CUDA(cudaSetDevice(h->device));
     const int cls = h->per_mode ? s - h->first : 0;
-    const size_t par = (size_t)(k & 1);
+    const size_t par = (size_t)(k % tk_handle::NBUF);
     if (theta) TK_CUDA(cudaMemcpy(theta, h->theta.p + (par * h->ncls + cls) * h->ncol, 8 * (size_t)k, cudaMemcpyDeviceToHost));
     if (Q) {
         std::vector<double> q((size_t)h->ldq * k);

@@ -280,9 +280,75 @@ def test_compress_and_residual_phases(tk, orc, tables, gpu, d, n, nmax, per_mode
     slv.close()
 
 
+@pytest.mark.parametrize("d,n,nmax,per_mode", [(5, 200, 24, False), (3, 150, 16, True)])
+def test_nonsym_compress_and_residual_phases(tk, orc, gpu, d, n, nmax, per_mode):
+    """NonSymInstance / ConvDiff / TensorArnoldi: the batched Taylor scaling-and-squaring exponential of the
+    Hessenberg matrix against the oracle's Pade expm (what Julia's exp(::Matrix) is), term by term."""
+    rng = np.random.default_rng(77 + d)
+    A = tk.assemble_matrix(n, tk.ConvDiff)
+    if per_mode:
+        b = orc.normalize_rhs([rng.random(n) for _ in range(d)])
+    else:
+        one = rng.random(n)
+        b = orc.normalize_rhs([one] * d)
+    flags = 0 if per_mode else tk.TK_FLAG_REFERENCE_H1
+    slv = make_solver(tk, [A] * d, b, nmax, tk.TensorArnoldi, tk.NonSymInstance, tk.ConvDiff, flags=flags, tol=1e-9)
+    slv.begin()
+    Ao = orc.assemble_matrix(n, orc.CONVDIFF)
+    S = orc.OracleSolve([Ao] * d, b, 1e-9, nmax, orc.ARNOLDI, orc.NONSYM, orc.CONVDIFF, None, per_mode=per_mode,
+                        ignore_breakdown=True)
+    for k in range(2, nmax + 1):
+        slv.step_bases(k)
+        slv.compress(k)
+        out = slv.residual(k, 0.0)
+        S.iterate()
+        _check_iteration(out, S.detail[k], k)
+        if k in (2, 7, nmax):
+            for s in (0, d - 1):
+                Y = slv.get_Y(s, k)
+                assert Y.shape == S.lastY[s].shape
+                assert rel(Y, S.lastY[s]) < 1e-10
+    slv.close()
+
+
+def test_sym_instance_with_arnoldi_basis(tk, orc, tables, gpu):
+    """TensorArnoldi on a SymInstance system: the compressed solve reads Symmetric(H_1, :L) of the Hessenberg matrix
+    (tensor_struct.jl:259) while Z = H Y uses the full H (utils.jl:247)."""
+    d, n, nmax = 4, 160, 18
+    rng = np.random.default_rng(9)
+    one = rng.random(n)
+    b = orc.normalize_rhs([one] * d)
+    A = tk.assemble_matrix(n, tk.Laplace)
+    slv = make_solver(tk, [A] * d, b, nmax, tk.TensorArnoldi, tk.SymInstance, tk.Laplace)
+    slv.begin()
+    S = orc.OracleSolve([orc.assemble_matrix(n, orc.LAPLACE)] * d, b, 1e-8, nmax, orc.ARNOLDI, orc.SYM, orc.LAPLACE,
+                        tables, ignore_breakdown=True)
+    for k in range(2, nmax + 1):
+        slv.step_bases(k)
+        slv.compress(k)
+        out = slv.residual(k, 0.0)
+        S.iterate()
+        _check_iteration(out, S.detail[k], k)
+    slv.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # whole solves through the reference-shaped API
 # ---------------------------------------------------------------------------------------------
+def test_solve_matches_reference_history_convdiff_d5(tk, gpu):
+    """The reference's own stored run (Julia, nonsym_new d=5: ConvDiff n=200, TensorArnoldi, tol 1e-9): the
+    histories agree while the estimate is well conditioned.  39 terms at k=2 growing to ~100 at k=60."""
+    g = golden("nonsym_new")
+    d, n, nmax = 5, 200, 60
+    A = tk.KroneckerMatrix.gallery(tk.NonSymInstance, d, n, tk.ConvDiff)
+    system = tk.TensorizedSystem(tk.NonSymInstance, A, [g["rhs_d5"]] * d)
+    cd = tk.solve_tensorized_system(system, nmax, tk.TensorArnoldi, 1e-9, verbose=False)
+    rr, pr = g["relres_d5"], g["projres_d5"]
+    assert cd.status == tk.TK_NMAX
+    k = np.arange(2, nmax + 1)
+    assert np.max(np.abs(cd.relative_residual_norm[k - 1] - rr[k - 1]) / rr[k - 1]) < 1e-9
+    assert np.max(np.abs(cd.projected_residual_norm[k - 1] - pr[k - 1]) / np.abs(pr[k - 1])) < 1e-8
+
 def test_solve_matches_reference_history_laplace_d5(tk, gpu):
     """The reference's own stored run (Julia, laplace_new d=5, tol 1e-9, nmax 199): same relative residuals."""
     g = golden("laplace_new")
