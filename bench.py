@@ -162,7 +162,11 @@ def run_reference(a):
 # ---------------------------------------------------------------------------------------------
 def run_b200(a):
     # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/tk_nccl_%h_%p.log")
+    # Only the one JSON line may reach stdout (NCCL prints its version banner there): park fd 1 on stderr until
+    # the line is ready.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     tk = entry.load_package()
@@ -276,6 +280,11 @@ def run_b200(a):
             dist.destroy_process_group()
         return 0
 
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+
     iters = a.steps * (nmax - 1)
     value = iters / (dev_ms / 1e3)
     peak, peak_kind = measured_peak()
@@ -307,7 +316,7 @@ def run_b200(a):
     if world == 1 and not a.no_cpu_baseline:
         cb, _ = cpu_arm(a, a.cpu_sample_modes)
         line["cpu_baseline"] = cb
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

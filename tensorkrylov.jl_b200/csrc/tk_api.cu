@@ -411,7 +411,8 @@ static double op_bytes_per_row(const tk_handle* h) {
 
 template <int CPM>
 static int launch_ttr_t(tk_handle* h, int k, int threads, size_t smem) {
-    TK_TRY(allow_smem(lanczos_ttr_kernel<CPM>, smem));
+    auto kernel = lanczos_ttr_kernel<CPM>;
+    TK_TRY(allow_smem(kernel, smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(h->dk * CPM);
     cfg.blockDim = dim3(threads);
@@ -423,7 +424,7 @@ static int launch_ttr_t(tk_handle* h, int k, int threads, size_t smem) {
     cfg.attrs = attr;
     cfg.numAttrs = CPM > 1 ? 1 : 0;
     KrylovParams p = h->kp();
-    TK_CUDA(cudaLaunchKernelEx(&cfg, lanczos_ttr_kernel<CPM>, p, k));
+    TK_CUDA(cudaLaunchKernelEx(&cfg, kernel, p, k));
     h->launches++;
     return 0;
 }
