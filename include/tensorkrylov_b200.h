@@ -135,6 +135,8 @@ int tk_solve(tk_handle* h, double tol, int32_t* status, int64_t* niter, int32_t*
  * or after any exit when force != 0 (uses the last iteration's y). */
 int tk_solution_rank(tk_handle* h, int32_t* t);
 int tk_get_solution(tk_handle* h, int32_t s, double* lambda, double* fmat, int32_t force);
+/* all local modes at once: fmat = [count][n*t], mode-major, each block n x t column-major (one D2H copy) */
+int tk_get_solution_all(tk_handle* h, double* lambda, double* fmat, int32_t force);
 
 /* ---- test-only single-phase entry points and state readers (parity/debug) */
 int tk_begin(tk_handle* h);                 /* orthonormalize!(decomp, b) + initialize_compressed_rhs: k = 1 */

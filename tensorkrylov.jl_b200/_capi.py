@@ -28,7 +28,7 @@ EXPORTS = [
     "tk_tables_load", "tk_tables_sym_lookup", "tk_nonsym_coefficients", "tk_laplace_extremes",
     "tk_comm_unique_id", "tk_create", "tk_destroy", "tk_release_cache", "tk_local_modes", "tk_needs_mode",
     "tk_set_operator_csc", "tk_set_operator_dense", "tk_share_operator", "tk_set_rhs", "tk_set_rhs_all",
-    "tk_set_schedule", "tk_schedule_laplace", "tk_solve", "tk_solution_rank", "tk_get_solution",
+    "tk_set_schedule", "tk_schedule_laplace", "tk_solve", "tk_solution_rank", "tk_get_solution", "tk_get_solution_all",
     "tk_begin", "tk_step_bases", "tk_compress", "tk_residual",
     "tk_get_H", "tk_get_V", "tk_get_bt", "tk_get_Y", "tk_get_eig", "tk_get_orth_state",
     "tk_tridiag_eig_batched", "tk_get_timing", "tk_launch_count",
@@ -74,6 +74,7 @@ def _load():
         "tk_solve": (C.c_int, [p, f64, pi32, pi64, pi32, pd, pd, pd]),
         "tk_solution_rank": (C.c_int, [p, pi32]),
         "tk_get_solution": (C.c_int, [p, i32, pd, pd, i32]),
+        "tk_get_solution_all": (C.c_int, [p, pd, pd, i32]),
         "tk_begin": (C.c_int, [p]),
         "tk_step_bases": (C.c_int, [p, i32]),
         "tk_compress": (C.c_int, [p, i32]),

@@ -287,11 +287,9 @@ class Solver:
         t = C.c_int32()
         check(lib.tk_solution_rank(self.h, C.byref(t)))
         lam = np.zeros(t.value)
-        fmat = {}
-        for s in range(self.first, self.first + self.count):
-            F = np.zeros((self.n, t.value), order="F")
-            check(lib.tk_get_solution(self.h, s, dptr(lam), dptr(F), 1 if force else 0))
-            fmat[s] = F
+        buf = np.empty((max(self.count, 1), t.value, self.n))      # [mode][column][row] = n x t column-major per mode
+        check(lib.tk_get_solution_all(self.h, dptr(lam), dptr(buf), 1 if force else 0))
+        fmat = {self.first + i: buf[i].T for i in range(self.count)}
         return lam, fmat
 
     # test-only phases and readers

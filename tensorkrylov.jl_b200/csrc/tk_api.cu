@@ -1299,6 +1299,36 @@ int tk_get_solution(tk_handle* h, int32_t s, double* lambda, double* fmat, int32
     return 0;
 }
 
+int tk_get_solution_all(tk_handle* h, double* lambda, double* fmat, int32_t force) {
+    if (!h) return set_error(TK_EINVAL, "null handle");
+    if (h->last_k < 2) return set_error(TK_ESTATE, "no compressed solution available");
+    TK_CUDA(cudaSetDevice(h->device));
+    int st = ST_RUNNING, tk_ = 0;
+    TK_CUDA(cudaMemcpy(&st, h->status_d.p, sizeof(int), cudaMemcpyDeviceToHost));
+    TK_CUDA(cudaMemcpy(&tk_, h->term_k_d.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st != ST_CONVERGED && !force) return set_error(TK_ESTATE, "solve did not converge (status %d); pass force to read the last iterate", st);
+    int k = h->last_k;
+    if (st != ST_RUNNING && tk_ >= 2) k = std::min(k, tk_);
+    const SchedEntry& se = h->sched[k];
+    const int t = se.t, tld = (t + 3) & ~3;
+    if (lambda) {
+        const double lam_inv = 1.0 / se.lambda_min;
+        for (int j = 0; j < t; ++j) lambda[j] = lam_inv * h->omega_pool[se.off + j];
+    }
+    if (!fmat || h->dl == 0) return 0;
+    DevBuf<double> X;
+    TK_TRY(X.alloc((size_t)h->dl * h->n * t, false));
+    dim3 grid((h->n + 255) / 256, (t + BM_TJ - 1) / BM_TJ);
+    const size_t smem = (size_t)k * BM_TJ * 8;
+    for (int sl = 0; sl < h->dl; ++sl)
+        basis_mul_kernel<<<grid, 256, smem, h->stream>>>(h->V.p + (size_t)sl * h->ncol * h->ldv, h->ldv, h->n, k,
+                                                         h->Y.p + (size_t)sl * h->ystride, tld, t, X.p + (size_t)sl * h->n * t);
+    TK_CUDA(cudaGetLastError());
+    TK_CUDA(cudaMemcpyAsync(fmat, X.p, 8 * (size_t)h->dl * h->n * t, cudaMemcpyDeviceToHost, h->stream));
+    TK_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 int tk_get_H(tk_handle* h, int32_t s, double* H) {
     bool local = false;
     TK_TRY(check_mode(h, s, &local));

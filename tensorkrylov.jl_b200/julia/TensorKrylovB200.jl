@@ -1,0 +1,127 @@
+# TensorKrylovB200.jl -- the reference-side binding of libtensorkrylov_b200.so.
+#
+# Drop-in for `tensorkrylov!` (TensorKrylov.jl src/tensor_krylov_method.jl:36-125): same signature, same
+# ConvergenceData conventions, same three exits.  Load it after `using TensorKrylov`; it adds one method,
+# `tensorkrylov_b200!`, and (optionally) re-points `solve_tensorized_system` at it.
+#
+# This file cannot be executed in the build image (no Julia there); every symbol it binds is exercised through
+# ctypes by the test-suite (tests/test_host_cpu.py::test_cabi_exports_every_declared_symbol and the -m gpu tests).
+module TensorKrylovB200
+
+using TensorKrylov
+using TensorKrylov: KronMat, KronProd, ConvergenceData, KruskalTensor, TensorDecomposition,
+                    TensorLanczos, TensorLanczosReorth, TensorArnoldi, SymInstance, NonSymInstance,
+                    MatrixGallery, LaplaceDense, Laplace, ConvDiff, EigValMat, RandSPD,
+                    SpectralData, ApproximationData, update_data!, dimensions
+using SparseArrays, LinearAlgebra
+
+const libtk = get(ENV, "TENSORKRYLOV_B200_LIB", "libtensorkrylov_b200.so")
+
+const TK_FLAG_REFERENCE_H1 = Cint(1)
+
+instance_code(::Type{SymInstance})    = Cint(0)
+instance_code(::Type{NonSymInstance}) = Cint(1)
+class_code(::Type{LaplaceDense}) = Cint(0); class_code(::Type{Laplace})   = Cint(1)
+class_code(::Type{ConvDiff})     = Cint(2); class_code(::Type{EigValMat}) = Cint(3)
+class_code(::Type{RandSPD})      = Cint(4); class_code(::Type{<:MatrixGallery}) = Cint(5)
+variant_code(::Type{<:TensorLanczos})       = Cint(0)
+variant_code(::Type{<:TensorLanczosReorth}) = Cint(1)
+variant_code(::Type{<:TensorArnoldi})       = Cint(2)
+
+lasterror() = unsafe_string(ccall((:tk_last_error, libtk), Cstring, ()))
+check(rc::Cint) = rc == 0 ? nothing : error("libtensorkrylov_b200: ", lasterror())
+
+function set_operator!(h::Ptr{Cvoid}, s::Int, A::SparseMatrixCSC{Float64, Int64})
+    # Julia's SparseMatrixCSC goes over verbatim: 1-based Int64 colptr/rowval
+    check(ccall((:tk_set_operator_csc, libtk), Cint,
+                (Ptr{Cvoid}, Int32, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+                h, s - 1, size(A, 1), A.colptr, A.rowval, A.nzval))
+end
+set_operator!(h, s, A::Symmetric{Float64, Matrix{Float64}}) =
+    check(ccall((:tk_set_operator_dense, libtk), Cint, (Ptr{Cvoid}, Int32, Int64, Ptr{Float64}, Cchar),
+                h, s - 1, size(A, 1), parent(A), A.uplo == 'L' ? 'L' : 'F'))
+set_operator!(h, s, A::Matrix{Float64}) =
+    check(ccall((:tk_set_operator_dense, libtk), Cint, (Ptr{Cvoid}, Int32, Int64, Ptr{Float64}, Cchar),
+                h, s - 1, size(A, 1), A, 'F'))
+
+"""
+    tensorkrylov_b200!(convergence_data, A, b, tol, nmax, orthonormalization_type; device = 0, flags = REFERENCE_H1)
+
+Same contract as `tensorkrylov!`: returns the `KruskalTensor` x on convergence, `nothing` otherwise; on
+`CompressedNormBreakdown` prints the reference's message, sets `niterations = k - 1` and `resize!`s the histories.
+"""
+function tensorkrylov_b200!(convergence_data::ConvergenceData{T}, A::KronMat{matT, U}, b::KronProd{T}, tol::T, nmax::Int,
+                            orthonormalization_type::Type{<:TensorDecomposition};
+                            device::Int = 0, flags::Cint = TK_FLAG_REFERENCE_H1) where {matT, T<:Float64, U}
+    d  = length(A)
+    ns = Int64.(dimensions(A))
+    href = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:tk_create, libtk), Cint,
+                (Ref{Ptr{Cvoid}}, Int32, Ptr{Int64}, Int32, Int32, Int32, Int32, Int32, Int32, Int32, Int32, Ptr{Cvoid}),
+                href, d, ns, nmax, instance_code(U), class_code(A.matrixclass), variant_code(orthonormalization_type),
+                flags, device, 0, 1, C_NULL))
+    h = href[]
+    try
+        # operators: the reference aliases one matrix object d times (tensor_struct.jl:208-210)
+        first_of = IdDict{Any, Int}()
+        for s in 1:d
+            if haskey(first_of, A[s])
+                check(ccall((:tk_share_operator, libtk), Cint, (Ptr{Cvoid}, Int32, Int32), h, s - 1, first_of[A[s]] - 1))
+            else
+                set_operator!(h, s, A[s]); first_of[A[s]] = s
+            end
+        end
+        for s in 1:d
+            check(ccall((:tk_set_rhs, libtk), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64), h, s - 1, b[s], length(b[s])))
+        end
+        # exp-sum schedule: exactly the reference's two update_data! calls, hoisted out of the loop
+        # (they depend on A_1, d, tol and k only -- tensor_krylov_method.jl:72-73)
+        spectraldata = SpectralData{matT, T, U}(A, nmax)
+        approxdata   = ApproximationData{T, U}(tol)
+        for k in 2:nmax
+            update_data!(spectraldata, d, A.matrixclass())
+            update_data!(approxdata, spectraldata)
+            check(ccall((:tk_set_schedule, libtk), Cint, (Ptr{Cvoid}, Int32, Float64, Int32, Ptr{Float64}, Ptr{Float64}),
+                        h, k, spectraldata.λ_min[k], length(approxdata.ω), approxdata.α, approxdata.ω))
+        end
+        status = Ref{Int32}(0); niter = Ref{Int64}(0); termk = Ref{Int32}(0)
+        check(ccall((:tk_solve, libtk), Cint,
+                    (Ptr{Cvoid}, Float64, Ref{Int32}, Ref{Int64}, Ref{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                    h, tol, status, niter, termk, convergence_data.relative_residual_norm,
+                    convergence_data.projected_residual_norm, convergence_data.orthogonality_data))
+        if status[] == 2                      # CompressedNormBreakdown, tensor_krylov_method.jl:85-96
+            println("Early termination at k = " * string(termk[]) * " due to compressed norm breakdown")
+            convergence_data.niterations = niter[]
+            resize!(convergence_data, convergence_data.niterations)
+            return nothing
+        elseif status[] == 0                  # converged, :108-118
+            tref = Ref{Int32}(0)
+            check(ccall((:tk_solution_rank, libtk), Cint, (Ptr{Cvoid}, Ref{Int32}), h, tref))
+            t = Int(tref[])
+            x = KruskalTensor{T}(ones(t), [zeros(Int(ns[s]), t) for s in 1:d])
+            for s in 1:d
+                check(ccall((:tk_get_solution, libtk), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Int32),
+                            h, s - 1, x.lambda, x.fmat[s], 0))
+            end
+            println("Convergence")
+            return x
+        elseif status[] == 3
+            error("NaN in the residual estimate at k = ", termk[])
+        end
+        println("No convergence")             # :122
+        return nothing
+    finally
+        ccall((:tk_destroy, libtk), Cvoid, (Ptr{Cvoid},), h)
+    end
+end
+
+"Route the reference's entry point (system.jl:65-83) through the GPU library."
+function solve_tensorized_system_b200(system, nmax::Int, orth::Type{<:TensorDecomposition}, tol = 1e-9; kw...)
+    convergencedata = ConvergenceData{typeof(tol)}(nmax)
+    tensorkrylov_b200!(convergencedata, system.A, system.b, tol, nmax, orth; kw...)
+    return convergencedata
+end
+
+export tensorkrylov_b200!, solve_tensorized_system_b200
+
+end # module
