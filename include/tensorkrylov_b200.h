@@ -154,7 +154,7 @@ int tk_get_orth_state(tk_handle* h, int32_t s, double* S /* running ||V'V - I||_
 /* batched symmetric tridiagonal eigensolver on its own (kernel 2): nb problems of order k;
  * diag[nb][k], sub[nb][k-1] -> theta[nb][k], Q[nb][k*k] col-major (may be NULL). */
 int tk_tridiag_eig_batched(int32_t device, int32_t nb, int32_t k, const double* diag, const double* sub,
-                           double* theta, double* Q);
+                           double* theta, double* Q, int32_t* fallbacks /* problems redone by the QL fallback, may be NULL */);
 
 /* which: 0 = 3-term Lanczos step, 1 = orthogonality-monitor Gram row, 2 = Arnoldi/MGS step,
  * 3 = eigensolver, 4 = CP assembly + Gram, 5 = cross-mode combine, 6 = the whole last tk_solve

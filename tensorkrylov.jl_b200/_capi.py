@@ -85,7 +85,7 @@ def _load():
         "tk_get_Y": (C.c_int, [p, i32, i32, pd, pi32]),
         "tk_get_eig": (C.c_int, [p, i32, i32, pd, pd]),
         "tk_get_orth_state": (C.c_int, [p, i32, pd, pi32]),
-        "tk_tridiag_eig_batched": (C.c_int, [i32, i32, i32, pd, pd, pd, pd]),
+        "tk_tridiag_eig_batched": (C.c_int, [i32, i32, i32, pd, pd, pd, pd, pi32]),
         "tk_get_timing": (C.c_int, [p, i32, pd, pi64, pd]),
         "tk_launch_count": (C.c_int, [p, pi64]),
     }

@@ -348,15 +348,19 @@ class Solver:
         return n.value
 
 
-def tridiag_eig_batched(diag, sub, device=0, vectors=True):
-    """Kernel (2) on its own: diag (nb, k), sub (nb, k-1) -> theta (nb, k), Q (nb, k, k) with Q[p][:, i] eigenvector i."""
+def tridiag_eig_batched(diag, sub, device=0, vectors=True, info=None):
+    """Kernel (2) on its own: diag (nb, k), sub (nb, k-1) -> theta (nb, k), Q (nb, k, k) with Q[p][:, i] eigenvector i.
+    info (a dict) receives the number of problems the QL fallback had to redo."""
     diag = _capi.as_f64(np.atleast_2d(diag))
     nb, k = diag.shape
     sub = _capi.as_f64(np.atleast_2d(sub)) if k > 1 else np.zeros((nb, 0))
     theta = np.zeros((nb, k))
     Q = np.zeros((nb, k, k)) if vectors else None
+    fb = C.c_int32(0)
     check(lib.tk_tridiag_eig_batched(device, nb, k, dptr(diag), dptr(sub) if k > 1 else None, dptr(theta),
-                                     dptr(Q) if vectors else None))
+                                     dptr(Q) if vectors else None, C.byref(fb)))
+    if info is not None:
+        info["fallbacks"] = fb.value
     if vectors:
         Q = np.transpose(Q, (0, 2, 1)).copy()   # stored column-major per problem
     return theta, Q

@@ -237,6 +237,8 @@ struct tk_handle {
 
     // compressed solve / residual
     DevBuf<double> theta, Q, Y, Z, E, bbm, partials, gathered, bnorm_d, relres_d, projres_d, orth_d, detail_d;
+    DevBuf<double> eig_scratch;         // second k x k plane per eigenproblem (bisection kernel), same ring as Q
+    DevBuf<int> eig_need;               // per problem: 1 if the QL fallback must recompute it
     DevBuf<double> exW;                 // NonSymInstance: workspace of the batched matrix exponential
     DevBuf<int> ex_nsq, ex_where, cls_mode_d;
     int ex_ld = 0;
@@ -361,6 +363,8 @@ static int alloc_work(tk_handle* h) {
     h->ldq = (h->ncol + 1) & ~1;
     TK_TRY(h->theta.alloc(tk_handle::NBUF * (size_t)h->ncls * h->ncol));   // ring: eig(k+1..) overlap assembly(k)
     TK_TRY(h->Q.alloc(tk_handle::NBUF * (size_t)h->ncls * h->ldq * h->ldq));
+    TK_TRY(h->eig_scratch.alloc(tk_handle::NBUF * (size_t)h->ncls * h->ldq * h->ldq, false));
+    TK_TRY(h->eig_need.alloc(tk_handle::NBUF * (size_t)h->ncls));
     h->ystride = (long long)kmax * tld;
     TK_TRY(h->Y.alloc((size_t)h->dl * h->ystride));
     TK_TRY(h->Z.alloc((size_t)h->dl * h->ystride));
@@ -547,16 +551,38 @@ static int enqueue_step_bases(tk_handle* h, int k) {
     return 0;
 }
 
+// Kernel (2): bisection + twisted factorisation first; the QL kernel runs right behind it on the problems the first
+// one flags (tight clusters, degenerate spectra).  TK_EIG_MODE=1 forces QL for everything.
 static int launch_eig(const double* T, long long tstride, int ncol, int k, int nprob, double* theta,
-                      int thstride, double* Q, long long qstride, int ldq, const int* status, int* fail, cudaStream_t st) {
+                      int thstride, double* Q, long long qstride, int ldq, const int* status, int* fail, double* scratch,
+                      int* need, cudaStream_t st, long long* launches) {
     if (k > 2048) return set_error(TK_EUNSUPPORTED, "eigensolver supports k <= 2048");
+    const bool bisect = env_int("TK_EIG_MODE", 0) == 0 && k <= 1024 && scratch && need;
+    if (bisect) {
+        const int threads = ((k + 31) / 32) * 32;
+        const size_t smem = ((size_t)5 * k + 2) * 8;
+        if (threads <= 256) {
+            TK_TRY(allow_smem(tridiag_eig_bisect_kernel<256>, smem));
+            tridiag_eig_bisect_kernel<256><<<nprob, threads, smem, st>>>(T, tstride, ncol, k, theta, thstride, Q, scratch, qstride,
+                                                                       ldq, status, need);
+        } else if (threads <= 512) {
+            TK_TRY(allow_smem(tridiag_eig_bisect_kernel<512>, smem));
+            tridiag_eig_bisect_kernel<512><<<nprob, threads, smem, st>>>(T, tstride, ncol, k, theta, thstride, Q, scratch, qstride,
+                                                                       ldq, status, need);
+        } else {
+            TK_TRY(allow_smem(tridiag_eig_bisect_kernel<1024>, smem));
+            tridiag_eig_bisect_kernel<1024><<<nprob, threads, smem, st>>>(T, tstride, ncol, k, theta, thstride, Q, scratch, qstride,
+                                                                        ldq, status, need);
+        }
+        TK_CUDA(cudaGetLastError());
+        if (launches) ++*launches;
+    }
     // rows of Q per CTA: as many as fit in shared memory next to the per-warp (d, e) copies
     const size_t budget = 200 * 1024;
     int rows = std::min(256, ((k + 31) / 32) * 32);
     while (rows > 8) {
         const int nwarp = (rows + 31) / 32;
-        const int ldz = rows >= 32 ? rows : rows;
-        if ((size_t)nwarp * 2 * k * 8 + (size_t)k * ldz * 8 <= budget) break;
+        if ((size_t)nwarp * 2 * k * 8 + (size_t)k * rows * 8 <= budget) break;
         rows = rows > 32 ? rows - 32 : rows / 2;
     }
     const int nwarp = (rows + 31) / 32;
@@ -566,8 +592,9 @@ static int launch_eig(const double* T, long long tstride, int ncol, int k, int n
     TK_TRY(allow_smem(tridiag_eig_kernel, smem));
     const int nrb = (k + rows - 1) / rows;
     tridiag_eig_kernel<<<dim3(nprob, nrb), nwarp * 32, smem, st>>>(T, tstride, ncol, k, rows, ldz, theta, thstride, Q, qstride,
-                                                                 ldq, status, fail);
+                                                                 ldq, status, fail, bisect ? need : nullptr);
     TK_CUDA(cudaGetLastError());
+    if (launches) ++*launches;
     return 0;
 }
 
@@ -597,9 +624,10 @@ static int enqueue_eig(tk_handle* h, int k) {
     CompressParams c = make_cp(h, k);
     cudaStream_t st = h->stream3[k % tk_handle::NEIG];
     TimedScope ts(h, TM_EIG, 0.0, st);
+    const size_t ring = (size_t)(k % tk_handle::NBUF);
     TK_TRY(launch_eig(Tsrc, 3LL * h->ncol, h->ncol, k, h->ncls, const_cast<double*>(c.theta), h->ncol, const_cast<double*>(c.Q),
-                      c.qstride, h->ldq, h->status_d.p, h->eigfail_d.p, st));
-    h->launches++;
+                      c.qstride, h->ldq, h->status_d.p, h->eigfail_d.p, h->eig_scratch.p + ring * h->ncls * h->ldq * h->ldq,
+                      h->eig_need.p + ring * h->ncls, st, &h->launches));
     return 0;
 }
 
@@ -1417,7 +1445,8 @@ int tk_get_orth_state(tk_handle* h, int32_t s, double* S, int32_t* fallbacks) {
     return 0;
 }
 
-int tk_tridiag_eig_batched(int32_t device, int32_t nb, int32_t k, const double* diag, const double* sub, double* theta, double* Q) {
+int tk_tridiag_eig_batched(int32_t device, int32_t nb, int32_t k, const double* diag, const double* sub, double* theta, double* Q,
+                           int32_t* fallbacks) {
     if (nb < 1 || k < 1 || !diag || !theta || (k > 1 && !sub)) return set_error(TK_EINVAL, "bad arguments");
     TK_CUDA(cudaSetDevice(device));
     const int ncol = k;
@@ -1426,14 +1455,23 @@ int tk_tridiag_eig_batched(int32_t device, int32_t nb, int32_t k, const double* 
         std::memcpy(&T[(size_t)p * 2 * ncol], diag + (size_t)p * k, 8 * (size_t)k);
         if (k > 1) std::memcpy(&T[(size_t)p * 2 * ncol + ncol], sub + (size_t)p * (k - 1), 8 * (size_t)(k - 1));
     }
-    DevBuf<double> Td, thd, Qd;
-    DevBuf<int> fail;
+    DevBuf<double> Td, thd, Qd, Sd;
+    DevBuf<int> fail, need;
     TK_TRY(Td.alloc(T.size(), false));
     TK_TRY(thd.alloc((size_t)nb * k));
     TK_TRY(Qd.alloc((size_t)nb * k * k));
+    TK_TRY(Sd.alloc((size_t)nb * k * k, false));
     TK_TRY(fail.alloc(1));
+    TK_TRY(need.alloc(nb));
     TK_CUDA(cudaMemcpy(Td.p, T.data(), 8 * T.size(), cudaMemcpyHostToDevice));
-    TK_TRY(launch_eig(Td.p, 2LL * ncol, ncol, k, nb, thd.p, k, Qd.p, (long long)k * k, k, nullptr, fail.p, 0));
+    TK_TRY(launch_eig(Td.p, 2LL * ncol, ncol, k, nb, thd.p, k, Qd.p, (long long)k * k, k, nullptr, fail.p, Sd.p, need.p, 0, nullptr));
+    if (fallbacks) {
+        std::vector<int> nd(nb);
+        TK_CUDA(cudaMemcpy(nd.data(), need.p, 4 * (size_t)nb, cudaMemcpyDeviceToHost));
+        int c = 0;
+        for (int v : nd) c += v;
+        *fallbacks = c;
+    }
     TK_CUDA(cudaDeviceSynchronize());
     int f = 0;
     TK_CUDA(cudaMemcpy(&f, fail.p, 4, cudaMemcpyDeviceToHost));

@@ -24,8 +24,9 @@ namespace tk {
 __global__ void __launch_bounds__(256) tridiag_eig_kernel(const double* __restrict__ T, long long tstride, int ncol,
                                                           int k, int rows_per_blk, int ldz, double* theta, int thstride,
                                                           double* Q, long long qstride, int ldq, const int* status,
-                                                          int* fail) {
+                                                          int* fail, const int* need) {
     if (status && *status != ST_RUNNING) return;
+    if (need && !need[blockIdx.x]) return;      // fallback role: only the problems the bisection kernel flagged
     extern __shared__ double smem[];
     const int prob = blockIdx.x;
     const int row0 = blockIdx.y * rows_per_blk;
@@ -108,6 +109,249 @@ __global__ void __launch_bounds__(256) tridiag_eig_kernel(const double* __restri
     if (active) {
         double* Qg = Q + (long long)prob * qstride + row0 + lrow;
         for (int i = 0; i < k; ++i) Qg[(long long)i * ldq] = Z[(size_t)i * ldz + lrow];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel (2), primary variant: bisection + twisted factorisation, O(k) latency instead of the O(k^2) dependent
+// rotation chain of QL (B200's dependent-FP64 latency makes that chain ~230 ns per rotation).
+//   one CTA per problem, thread j <-> eigenvalue j (ascending)
+//   1. scale T by a power of two to norm <= 1; Gershgorin interval
+//   2. eigenvalue j by 8-way multisection on the Sturm count.  The count uses the division-free three-term
+//      recurrence p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2} (one dependent FMA per step, 7 independent chains per
+//      thread hide its latency), rescaled by a power of two every 8 steps
+//   3. eigenvector j from the twisted factorisation of T - theta_j I (Parlett-Dhillon): forward LDL' and backward
+//      UDU' sweeps (two interleaved division chains), twist at argmin |gamma_i|, then two one-multiply recurrences
+//   4. eigenvalues closer than 1e-3 ||T|| are re-orthogonalised against each other (modified Gram-Schmidt inside the
+//      cluster, one warp per cluster), as LAPACK's dstein does
+//   5. problems with gaps below 1e-9 ||T||, very large clusters or non-finite vectors raise need[prob]; the QL
+//      kernel, launched right behind, recomputes exactly those problems (and returns at once for the others)
+// scratch / Q: [prob][ldq*ldq]; during the kernel both are used as [component i][eigen index j] planes.
+// ------------------------------------------------------------------------------------------
+constexpr int BI_M = 7;        // interior points per multisection pass (8-way split)
+constexpr int BI_PASSES = 20;  // 8^20 > 2^57
+
+__device__ __forceinline__ double pow2i(int ex) {   // 2^ex for -1022 <= ex <= 1023
+    return __hiloint2double((1023 + ex) << 20, 0);
+}
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) tridiag_eig_bisect_kernel(const double* __restrict__ T, long long tstride,
+                                                                  int ncol, int k, double* theta, int thstride,
+                                                                  double* Q, double* scratch, long long qstride,
+                                                                  int ldq, const int* status, int* need) {
+    if (status && *status != ST_RUNNING) return;
+    extern __shared__ double smem[];
+    __shared__ double red[32];
+    __shared__ double tile[32][33];
+    __shared__ int nclus_s, bad_s;
+    const int prob = blockIdx.x, j = threadIdx.x, nthr = blockDim.x;
+    double* d = smem;             // k   scaled diagonal
+    double* e = smem + k;         // k   scaled sub-diagonal (e[k-1] = 0)
+    double* e2 = smem + 2 * k;    // k
+    double* th = smem + 3 * k;    // k   scaled eigenvalues
+    int* cstart = reinterpret_cast<int*>(smem + 4 * k);   // k+1 cluster boundaries
+    const double* Td = T + (long long)prob * tstride;
+    double* A = scratch + (long long)prob * qstride;   // plane [i*ldq + j]: D+ then z
+    double* B = Q + (long long)prob * qstride;         // plane [i*ldq + j]: D-; finally the transposed output
+    if (threadIdx.x == 0) { nclus_s = 0; bad_s = 0; }
+    // ---- 1. norm and scaling
+    double lo_g = 1e300, hi_g = -1e300;
+    for (int i = threadIdx.x; i < k; i += nthr) {
+        const double di = Td[i];
+        const double el = (i > 0) ? fabs(Td[ncol + i - 1]) : 0.0, er = (i < k - 1) ? fabs(Td[ncol + i]) : 0.0;
+        lo_g = fmin(lo_g, di - el - er);
+        hi_g = fmax(hi_g, di + el + er);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo_g = fmin(lo_g, __shfl_xor_sync(0xffffffffu, lo_g, o));
+        hi_g = fmax(hi_g, __shfl_xor_sync(0xffffffffu, hi_g, o));
+    }
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = lo_g; }
+    __syncthreads();
+    lo_g = red[0];
+    for (int w = 1; w < (nthr + 31) / 32; ++w) lo_g = fmin(lo_g, red[w]);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = hi_g; }
+    __syncthreads();
+    hi_g = red[0];
+    for (int w = 1; w < (nthr + 31) / 32; ++w) hi_g = fmax(hi_g, red[w]);
+    const double nrm = fmax(fabs(lo_g), fabs(hi_g));
+    int ex = 0;
+    if (nrm > 0.0 && nrm < 1e300) ex = ((__double2hiint(nrm) >> 20) & 0x7ff) - 1023 + 1;   // nrm < 2^ex
+    ex = max(-1000, min(1000, ex));
+    const double sc = pow2i(-ex), unsc = pow2i(ex);
+    for (int i = threadIdx.x; i < k; i += nthr) {
+        d[i] = Td[i] * sc;
+        const double ei = (i < k - 1) ? Td[ncol + i] * sc : 0.0;
+        e[i] = ei;
+        e2[i] = ei * ei;
+    }
+    __syncthreads();
+    const bool active = j < k;
+    const double EPS = 2.220446049250313e-16;
+    // ---- 2. multisection
+    double lo = lo_g * sc - 4.0 * EPS * k - 1e-300, hi = hi_g * sc + 4.0 * EPS * k + 1e-300;
+    if (active) {
+        for (int pass = 0; pass < BI_PASSES; ++pass) {
+            const double w = (hi - lo) * 0.125;
+            double x[BI_M], p[BI_M], pm[BI_M];
+            int cnt[BI_M];
+            bool neg[BI_M];
+#pragma unroll
+            for (int m = 0; m < BI_M; ++m) {
+                x[m] = lo + (m + 1) * w;
+                pm[m] = 1.0;
+                p[m] = d[0] - x[m];
+                neg[m] = p[m] < 0.0;         // p_1 == 0 counts as negative relative to p_0 = 1 > 0
+                if (p[m] == 0.0) neg[m] = true;
+                cnt[m] = neg[m] ? 1 : 0;
+            }
+            for (int i = 1; i < k; ++i) {
+                const double di = d[i], ee = e2[i - 1];
+#pragma unroll
+                for (int m = 0; m < BI_M; ++m) {
+                    const double pn = fma(di - x[m], p[m], -(ee * pm[m]));
+                    const bool ng = (pn < 0.0) || (pn == 0.0 && !neg[m]);
+                    cnt[m] += (ng != neg[m]) ? 1 : 0;
+                    neg[m] = ng;
+                    pm[m] = p[m];
+                    p[m] = pn;
+                }
+                if ((i & 7) == 7) {
+#pragma unroll
+                    for (int m = 0; m < BI_M; ++m) {
+                        const double big = fmax(fabs(p[m]), fabs(pm[m]));
+                        if (big > 0.0 && big < 1e300) {
+                            const int pe = ((__double2hiint(big) >> 20) & 0x7ff) - 1023;
+                            if (pe > 64 || pe < -64) {
+                                const double f = pow2i(max(-1000, min(1000, -pe)));
+                                p[m] *= f; pm[m] *= f;
+                            }
+                        }
+                    }
+                }
+            }
+            double nlo = lo, nhi = hi;
+            bool done = false;
+#pragma unroll
+            for (int m = 0; m < BI_M; ++m) {
+                if (!done) {
+                    if (cnt[m] <= j) nlo = x[m];       // at most j eigenvalues below x_m: eigenvalue j is >= x_m
+                    else { nhi = x[m]; done = true; }
+                }
+            }
+            lo = nlo; hi = nhi;
+        }
+        th[j] = 0.5 * (lo + hi);
+    }
+    __syncthreads();
+    // ---- 3. twisted factorisation
+    double nrm2 = 0.0;
+    if (active) {
+        const double t0 = th[j];
+        double dp = d[0] - t0, dm = d[k - 1] - t0;
+        if (dp == 0.0) dp = 1e-300;
+        if (dm == 0.0) dm = 1e-300;
+        A[(long long)0 * ldq + j] = dp;
+        B[(long long)(k - 1) * ldq + j] = dm;
+        for (int i = 0; i < k - 1; ++i) {
+            const int ib = k - 2 - i;
+            dp = (d[i + 1] - t0) - e2[i] / dp;
+            dm = (d[ib] - t0) - e2[ib] / dm;
+            if (dp == 0.0) dp = 1e-300;
+            if (dm == 0.0) dm = 1e-300;
+            A[(long long)(i + 1) * ldq + j] = dp;
+            B[(long long)ib * ldq + j] = dm;
+        }
+        int r = 0;
+        double best = 1e300;
+        for (int i = 0; i < k; ++i) {
+            const double gam = fabs(A[(long long)i * ldq + j] + B[(long long)i * ldq + j] - (d[i] - t0));
+            if (gam < best) { best = gam; r = i; }
+        }
+        double z = 1.0;
+        nrm2 = 1.0;
+        for (int i = r - 1; i >= 0; --i) {                 // z_i = -(e_i / D+_i) z_{i+1}
+            const double l = e[i] / A[(long long)i * ldq + j];
+            z = -l * z;
+            A[(long long)i * ldq + j] = z;
+            nrm2 = fma(z, z, nrm2);
+        }
+        z = 1.0;
+        for (int i = r; i < k - 1; ++i) {                  // z_{i+1} = -(e_i / D-_{i+1}) z_i
+            const double u = e[i] / B[(long long)(i + 1) * ldq + j];
+            z = -u * z;
+            A[(long long)(i + 1) * ldq + j] = z;
+            nrm2 = fma(z, z, nrm2);
+        }
+        A[(long long)r * ldq + j] = 1.0;
+        const double inv = rsqrt(nrm2);
+        if (!(nrm2 > 0.0) || !(nrm2 < 1e300) || inv != inv) atomicExch(&bad_s, 1);
+        for (int i = 0; i < k; ++i) A[(long long)i * ldq + j] *= inv;
+        theta[(long long)prob * thstride + j] = t0 * unsc;
+    }
+    __threadfence_block();
+    __syncthreads();
+    // ---- 4. clusters
+    if (threadIdx.x == 0) {
+        int nc = 0, start = 0;
+        for (int c = 1; c <= k; ++c) {
+            if (c == k || th[c] - th[c - 1] > 1e-3) {
+                if (c - start > 1) {
+                    cstart[2 * nc] = start; cstart[2 * nc + 1] = c; ++nc;
+                    if (c - start > 48) bad_s = 1;
+                }
+                start = c;
+            } else if (th[c] - th[c - 1] < 1e-9) {
+                bad_s = 1;
+            }
+        }
+        nclus_s = nc;
+    }
+    __syncthreads();
+    const int nclus = nclus_s;
+    if (nclus > 0 && !bad_s) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = nthr >> 5;
+        for (int c = warp; c < nclus; c += nwarp) {
+            const int c0 = cstart[2 * c], c1 = cstart[2 * c + 1];
+            for (int a = c0 + 1; a < c1; ++a) {
+                for (int b = c0; b < a; ++b) {
+                    double dot = 0.0;
+                    for (int i = lane; i < k; i += 32) dot = fma(A[(long long)i * ldq + b], A[(long long)i * ldq + a], dot);
+                    dot = warp_sum(dot);
+                    for (int i = lane; i < k; i += 32) A[(long long)i * ldq + a] = fma(-dot, A[(long long)i * ldq + b], A[(long long)i * ldq + a]);
+                    __syncwarp();
+                }
+                double nn = 0.0;
+                for (int i = lane; i < k; i += 32) nn = fma(A[(long long)i * ldq + a], A[(long long)i * ldq + a], nn);
+                nn = warp_sum(nn);
+                const double inv = rsqrt(nn);
+                if (!(nn > 1e-8)) { if (lane == 0) atomicExch(&bad_s, 1); }
+                for (int i = lane; i < k; i += 32) A[(long long)i * ldq + a] *= inv;
+                __syncwarp();
+            }
+        }
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (threadIdx.x == 0 && need) need[prob] = bad_s;
+    // ---- transpose into the output layout Q[j*ldq + i]
+    const int nt = (k + 31) / 32;
+    for (int tt = 0; tt < nt * nt; ++tt) {
+        const int ti = tt / nt, tj = tt % nt;      // components ti*32.., eigen indices tj*32..
+        for (int idx = threadIdx.x; idx < 1024; idx += nthr) {
+            const int r = idx >> 5, c = idx & 31;
+            const int i = ti * 32 + r, jj = tj * 32 + c;
+            tile[r][c] = (i < k && jj < k) ? A[(long long)i * ldq + jj] : 0.0;
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < 1024; idx += nthr) {
+            const int r = idx >> 5, c = idx & 31;          // r: eigen index in tile, c: component in tile
+            const int jj = tj * 32 + r, i = ti * 32 + c;
+            if (i < k && jj < k) B[(long long)jj * ldq + i] = tile[c][r];
+        }
+        __syncthreads();
     }
 }
 

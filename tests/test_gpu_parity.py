@@ -41,8 +41,14 @@ def make_solver(tk, A_list, b_list, nmax, variant, instance, cls, flags=None, to
 # ---------------------------------------------------------------------------------------------
 # kernel (2): batched symmetric tridiagonal eigensolver
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("k", [1, 2, 3, 5, 31, 32, 33, 64, 100, 130, 200, 256])
-def test_tridiag_eig(tk, gpu, k):
+@pytest.mark.parametrize("mode", ["bisect", "ql"])
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 31, 32, 33, 64, 100, 130, 200, 256, 300, 600])
+def test_tridiag_eig(tk, gpu, k, mode, monkeypatch):
+    """Both variants of kernel (2): bisection + twisted factorisation (primary) and implicit QL (fallback)."""
+    if mode == "ql":
+        if k > 256:
+            pytest.skip("QL at this size is covered by the fallback test; it takes seconds")
+        monkeypatch.setenv("TK_EIG_MODE", "1")
     rng = np.random.default_rng(k)
     nb = 3
     diag = rng.normal(size=(nb, k)) * 1e3
@@ -51,7 +57,10 @@ def test_tridiag_eig(tk, gpu, k):
     diag[0] = 2.0e8
     if k > 1:
         sub[0] = -1.0e8
-    theta, Q = tk.tridiag_eig_batched(diag, sub)
+    info = {}
+    theta, Q = tk.tridiag_eig_batched(diag, sub, info=info)
+    # dense random spectra at large k form clusters longer than the bisection kernel accepts: those go to QL
+    assert info["fallbacks"] == 0 or mode == "ql" or k >= 300
     for p in range(nb):
         T = np.diag(diag[p]) + np.diag(sub[p], -1) + np.diag(sub[p], 1) if k > 1 else np.diag(diag[p])
         w = np.linalg.eigvalsh(T)
@@ -68,7 +77,9 @@ def test_tridiag_eig_clustered_and_split(tk, gpu):
     sub = np.ones((1, k - 1))
     sub[0, 10] = 0.0
     sub[0, 25] = 1e-300
-    theta, Q = tk.tridiag_eig_batched(diag, sub)
+    info = {}
+    theta, Q = tk.tridiag_eig_batched(diag, sub, info=info)
+    assert info["fallbacks"] == 1      # degenerate pairs: the bisection kernel hands the problem to QL
     T = np.diag(diag[0]) + np.diag(sub[0], -1) + np.diag(sub[0], 1)
     assert np.max(np.abs(np.sort(theta[0]) - np.linalg.eigvalsh(T))) < 1e-13 * 40
     assert np.linalg.norm(Q[0].T @ Q[0] - np.eye(k)) < 1e-12
