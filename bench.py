@@ -249,6 +249,25 @@ def run_b200(a):
     fb = slv.orth_state(slv.first)[1] if slv.count else 0
     slv.close()
 
+    # ---- time-to-tolerance (second half of BASELINE.json's metric): parity mode, tol 1e-5 -- the only tolerance
+    # this configuration reaches: device time from first enqueue to the converged status
+    ttt = None
+    if a.d >= 256 and a.n >= 10000:
+        s2 = make(0 if a.per_mode else tk.TK_FLAG_REFERENCE_H1)
+        s2.set_operators([A1] * d); s2.set_rhs([b_np] * d); s2.set_schedule(A1, 1e-5)
+        best = None
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            r2 = s2.solve(1e-5)
+            wall = 1e3 * (time.perf_counter() - t0)
+            dev = maxr(s2.timing(6)[0])
+            if best is None or dev < best[0]:
+                best = (dev, wall)
+        ttt = {"tol": 1e-5, "status": r2["status"], "iterations": r2["term_k"], "device_ms": best[0], "call_ms": best[1],
+               "relres": float(r2["relres"][r2["term_k"] - 1]) if r2["term_k"] >= 1 else None}
+        s2.close()
+
     # ---- end-to-end arm: the public call with host buffers, H2D and D2H inside the timed region -----
     A = tk.KroneckerMatrix(tk.SymInstance, [A1] * d, tk.Laplace)
     def e2e_once():
@@ -303,6 +322,7 @@ def run_b200(a):
                 "ms_per_step": e2e_ms / a.steps,
                 "note": "handle creation (cudaMalloc of the bases), operator/rhs/schedule upload, solve, histories back"},
         "gpu_launches": launches,
+        "time_to_tol": ttt,
         "roofline": {"kernel": "gram_row_kernel (orthogonality monitor of the batched Lanczos step)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",

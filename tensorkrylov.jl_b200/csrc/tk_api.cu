@@ -407,9 +407,13 @@ static int allow_smem(K kernel, size_t bytes) {
 }
 
 // --- kernel (1) launches -------------------------------------------------------------------
+// Operator bytes one all-mode SpMV has to fetch from HBM, averaged per mode-row: an operator object aliased by
+// several modes (the reference aliases ONE matrix d times, tensor_struct.jl:208-210) is fetched once, not per mode.
 static double op_bytes_per_row(const tk_handle* h) {
+    std::set<int> distinct;
+    for (int s = 0; s < h->dk; ++s) distinct.insert(h->mode_op[s]);
     double acc = 0.0;
-    for (int s = 0; s < h->dk; ++s) acc += h->ops[h->mode_op[s]]->bytes_per_row();
+    for (int o : distinct) acc += h->ops[o]->bytes_per_row();
     return h->dk ? acc / h->dk : 0.0;
 }
 
@@ -559,21 +563,21 @@ static int launch_eig(const double* T, long long tstride, int ncol, int k, int n
     if (k > 2048) return set_error(TK_EUNSUPPORTED, "eigensolver supports k <= 2048");
     const bool bisect = env_int("TK_EIG_MODE", 0) == 0 && k <= 1024 && scratch && need;
     if (bisect) {
-        const int threads = ((k + 31) / 32) * 32;
+        // threads per eigenvalue during the multisection: as many as a 1024-thread CTA allows, at most 8
+        int tpe = 8;
+        while (tpe > 1 && k * tpe > 1024) tpe >>= 1;
+        const int threads = ((k * tpe + 31) / 32) * 32;
         const size_t smem = ((size_t)5 * k + 2) * 8;
-        if (threads <= 256) {
-            TK_TRY(allow_smem(tridiag_eig_bisect_kernel<256>, smem));
-            tridiag_eig_bisect_kernel<256><<<nprob, threads, smem, st>>>(T, tstride, ncol, k, theta, thstride, Q, scratch, qstride,
-                                                                       ldq, status, need);
-        } else if (threads <= 512) {
-            TK_TRY(allow_smem(tridiag_eig_bisect_kernel<512>, smem));
-            tridiag_eig_bisect_kernel<512><<<nprob, threads, smem, st>>>(T, tstride, ncol, k, theta, thstride, Q, scratch, qstride,
-                                                                       ldq, status, need);
-        } else {
-            TK_TRY(allow_smem(tridiag_eig_bisect_kernel<1024>, smem));
-            tridiag_eig_bisect_kernel<1024><<<nprob, threads, smem, st>>>(T, tstride, ncol, k, theta, thstride, Q, scratch, qstride,
-                                                                        ldq, status, need);
-        }
+#define TK_BISECT_LAUNCH(MT)                                                                                          \
+        do {                                                                                                          \
+            TK_TRY(allow_smem(tridiag_eig_bisect_kernel<MT>, smem));                                                  \
+            tridiag_eig_bisect_kernel<MT><<<nprob, threads, smem, st>>>(T, tstride, ncol, k, tpe, theta, thstride, Q, \
+                                                                      scratch, qstride, ldq, status, need);           \
+        } while (0)
+        if (threads <= 256) TK_BISECT_LAUNCH(256);
+        else if (threads <= 512) TK_BISECT_LAUNCH(512);
+        else TK_BISECT_LAUNCH(1024);
+#undef TK_BISECT_LAUNCH
         TK_CUDA(cudaGetLastError());
         if (launches) ++*launches;
     }

@@ -117,9 +117,9 @@ __global__ void __launch_bounds__(256) tridiag_eig_kernel(const double* __restri
 // rotation chain of QL (B200's dependent-FP64 latency makes that chain ~230 ns per rotation).
 //   one CTA per problem, thread j <-> eigenvalue j (ascending)
 //   1. scale T by a power of two to norm <= 1; Gershgorin interval
-//   2. eigenvalue j by 8-way multisection on the Sturm count.  The count uses the division-free three-term
-//      recurrence p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2} (one dependent FMA per step, 7 independent chains per
-//      thread hide its latency), rescaled by a power of two every 8 steps
+//   2. eigenvalue j by (tpe+1)-way multisection on the Sturm count, tpe <= 8 threads per eigenvalue with one
+//      interior point each.  The count uses the division-free three-term recurrence
+//      p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2} (one dependent FMA per step), rescaled by a power of two
 //   3. eigenvector j from the twisted factorisation of T - theta_j I (Parlett-Dhillon): forward LDL' and backward
 //      UDU' sweeps (two interleaved division chains), twist at argmin |gamma_i|, then two one-multiply recurrences
 //   4. eigenvalues closer than 1e-3 ||T|| are re-orthogonalised against each other (modified Gram-Schmidt inside the
@@ -128,16 +128,15 @@ __global__ void __launch_bounds__(256) tridiag_eig_kernel(const double* __restri
 //      kernel, launched right behind, recomputes exactly those problems (and returns at once for the others)
 // scratch / Q: [prob][ldq*ldq]; during the kernel both are used as [component i][eigen index j] planes.
 // ------------------------------------------------------------------------------------------
-constexpr int BI_M = 7;        // interior points per multisection pass (8-way split)
-constexpr int BI_PASSES = 20;  // 8^20 > 2^57
-
 __device__ __forceinline__ double pow2i(int ex) {   // 2^ex for -1022 <= ex <= 1023
     return __hiloint2double((1023 + ex) << 20, 0);
 }
 
+// TPE threads cooperate on one eigenvalue during the multisection (one interior point each: the dependent
+// Sturm chains of a pass then run in different lanes/warps instead of back to back in one in-order warp).
 template <int MAXT>
 __global__ void __launch_bounds__(MAXT) tridiag_eig_bisect_kernel(const double* __restrict__ T, long long tstride,
-                                                                  int ncol, int k, double* theta, int thstride,
+                                                                  int ncol, int k, int tpe, double* theta, int thstride,
                                                                   double* Q, double* scratch, long long qstride,
                                                                   int ldq, const int* status, int* need) {
     if (status && *status != ST_RUNNING) return;
@@ -145,12 +144,12 @@ __global__ void __launch_bounds__(MAXT) tridiag_eig_bisect_kernel(const double* 
     __shared__ double red[32];
     __shared__ double tile[32][33];
     __shared__ int nclus_s, bad_s;
-    const int prob = blockIdx.x, j = threadIdx.x, nthr = blockDim.x;
+    const int prob = blockIdx.x, nthr = blockDim.x;
     double* d = smem;             // k   scaled diagonal
     double* e = smem + k;         // k   scaled sub-diagonal (e[k-1] = 0)
     double* e2 = smem + 2 * k;    // k
     double* th = smem + 3 * k;    // k   scaled eigenvalues
-    int* cstart = reinterpret_cast<int*>(smem + 4 * k);   // k+1 cluster boundaries
+    int* cstart = reinterpret_cast<int*>(smem + 4 * k);   // cluster boundaries (pairs)
     const double* Td = T + (long long)prob * tstride;
     double* A = scratch + (long long)prob * qstride;   // plane [i*ldq + j]: D+ then z
     double* B = Q + (long long)prob * qstride;         // plane [i*ldq + j]: D-; finally the transposed output
@@ -188,67 +187,54 @@ __global__ void __launch_bounds__(MAXT) tridiag_eig_bisect_kernel(const double* 
         e2[i] = ei * ei;
     }
     __syncthreads();
-    const bool active = j < k;
     const double EPS = 2.220446049250313e-16;
-    // ---- 2. multisection
-    double lo = lo_g * sc - 4.0 * EPS * k - 1e-300, hi = hi_g * sc + 4.0 * EPS * k + 1e-300;
-    if (active) {
-        for (int pass = 0; pass < BI_PASSES; ++pass) {
-            const double w = (hi - lo) * 0.125;
-            double x[BI_M], p[BI_M], pm[BI_M];
-            int cnt[BI_M];
-            bool neg[BI_M];
-#pragma unroll
-            for (int m = 0; m < BI_M; ++m) {
-                x[m] = lo + (m + 1) * w;
-                pm[m] = 1.0;
-                p[m] = d[0] - x[m];
-                neg[m] = p[m] < 0.0;         // p_1 == 0 counts as negative relative to p_0 = 1 > 0
-                if (p[m] == 0.0) neg[m] = true;
-                cnt[m] = neg[m] ? 1 : 0;
-            }
+    // ---- 2. multisection: thread = (eigenvalue jj, interior point m); (tpe+1)-way split per pass
+    {
+        const int jj = threadIdx.x / tpe, m = threadIdx.x % tpe;
+        const bool act = jj < k;
+        const int jc = act ? jj : k - 1;
+        double lo = lo_g * sc - 4.0 * EPS * k - 1e-300, hi = hi_g * sc + 4.0 * EPS * k + 1e-300;
+        // interval shrinks by (tpe+1) per pass; stop at 2^-57 of the initial width
+        int passes = 57;
+        if (tpe == 2) passes = 36; else if (tpe == 4) passes = 25; else if (tpe == 8) passes = 18;
+        for (int pass = 0; pass < passes; ++pass) {
+            const double w = (hi - lo) / (double)(tpe + 1);
+            const double x = lo + (m + 1) * w;
+            double pm = 1.0, p = d[0] - x;
+            bool neg = (p < 0.0) || (p == 0.0);
+            int cnt = neg ? 1 : 0;
             for (int i = 1; i < k; ++i) {
-                const double di = d[i], ee = e2[i - 1];
-#pragma unroll
-                for (int m = 0; m < BI_M; ++m) {
-                    const double pn = fma(di - x[m], p[m], -(ee * pm[m]));
-                    const bool ng = (pn < 0.0) || (pn == 0.0 && !neg[m]);
-                    cnt[m] += (ng != neg[m]) ? 1 : 0;
-                    neg[m] = ng;
-                    pm[m] = p[m];
-                    p[m] = pn;
-                }
+                const double pn = fma(d[i] - x, p, -(e2[i - 1] * pm));
+                const bool ng = (pn < 0.0) || (pn == 0.0 && !neg);
+                cnt += (ng != neg) ? 1 : 0;
+                neg = ng;
+                pm = p;
+                p = pn;
                 if ((i & 7) == 7) {
-#pragma unroll
-                    for (int m = 0; m < BI_M; ++m) {
-                        const double big = fmax(fabs(p[m]), fabs(pm[m]));
-                        if (big > 0.0 && big < 1e300) {
-                            const int pe = ((__double2hiint(big) >> 20) & 0x7ff) - 1023;
-                            if (pe > 64 || pe < -64) {
-                                const double f = pow2i(max(-1000, min(1000, -pe)));
-                                p[m] *= f; pm[m] *= f;
-                            }
+                    const double big = fmax(fabs(p), fabs(pm));
+                    if (big > 0.0 && big < 1e300) {
+                        const int pe = ((__double2hiint(big) >> 20) & 0x7ff) - 1023;
+                        if (pe > 64 || pe < -64) {
+                            const double f = pow2i(max(-1000, min(1000, -pe)));
+                            p *= f; pm *= f;
                         }
                     }
                 }
             }
-            double nlo = lo, nhi = hi;
-            bool done = false;
-#pragma unroll
-            for (int m = 0; m < BI_M; ++m) {
-                if (!done) {
-                    if (cnt[m] <= j) nlo = x[m];       // at most j eigenvalues below x_m: eigenvalue j is >= x_m
-                    else { nhi = x[m]; done = true; }
-                }
+            // eigenvalue jc lies right of every point with cnt <= jc and left of every point with cnt > jc
+            double nlo = (cnt <= jc) ? x : lo, nhi = (cnt > jc) ? x : hi;
+            for (int o = 1; o < tpe; o <<= 1) {
+                nlo = fmax(nlo, __shfl_xor_sync(0xffffffffu, nlo, o));
+                nhi = fmin(nhi, __shfl_xor_sync(0xffffffffu, nhi, o));
             }
             lo = nlo; hi = nhi;
         }
-        th[j] = 0.5 * (lo + hi);
+        if (act && m == 0) th[jj] = 0.5 * (lo + hi);
     }
     __syncthreads();
-    // ---- 3. twisted factorisation
-    double nrm2 = 0.0;
-    if (active) {
+    // ---- 3. twisted factorisation: thread j <-> eigenvector j
+    const int j = threadIdx.x;
+    if (j < k) {
         const double t0 = th[j];
         double dp = d[0] - t0, dm = d[k - 1] - t0;
         if (dp == 0.0) dp = 1e-300;
@@ -264,31 +250,71 @@ __global__ void __launch_bounds__(MAXT) tridiag_eig_bisect_kernel(const double* 
             A[(long long)(i + 1) * ldq + j] = dp;
             B[(long long)ib * ldq + j] = dm;
         }
+        // twist index r = argmin |gamma_i|, gamma_i = D+_i + D-_i - (d_i - theta); 4 rows in flight
         int r = 0;
         double best = 1e300;
-        for (int i = 0; i < k; ++i) {
+        int i = 0;
+        for (; i + 3 < k; i += 4) {
+            const double a0 = A[(long long)i * ldq + j], a1 = A[(long long)(i + 1) * ldq + j],
+                         a2 = A[(long long)(i + 2) * ldq + j], a3 = A[(long long)(i + 3) * ldq + j];
+            const double b0 = B[(long long)i * ldq + j], b1 = B[(long long)(i + 1) * ldq + j],
+                         b2 = B[(long long)(i + 2) * ldq + j], b3 = B[(long long)(i + 3) * ldq + j];
+            const double g0 = fabs(a0 + b0 - (d[i] - t0)), g1 = fabs(a1 + b1 - (d[i + 1] - t0)),
+                         g2 = fabs(a2 + b2 - (d[i + 2] - t0)), g3 = fabs(a3 + b3 - (d[i + 3] - t0));
+            if (g0 < best) { best = g0; r = i; }
+            if (g1 < best) { best = g1; r = i + 1; }
+            if (g2 < best) { best = g2; r = i + 2; }
+            if (g3 < best) { best = g3; r = i + 3; }
+        }
+        for (; i < k; ++i) {
             const double gam = fabs(A[(long long)i * ldq + j] + B[(long long)i * ldq + j] - (d[i] - t0));
             if (gam < best) { best = gam; r = i; }
         }
-        double z = 1.0;
-        nrm2 = 1.0;
-        for (int i = r - 1; i >= 0; --i) {                 // z_i = -(e_i / D+_i) z_{i+1}
-            const double l = e[i] / A[(long long)i * ldq + j];
-            z = -l * z;
+        // z_r = 1; upward z_i = -(e_i / D+_i) z_{i+1}; downward z_{i+1} = -(e_i / D-_{i+1}) z_i.
+        // The divisions do not depend on z: four are issued together, then the four dependent multiplies.
+        double z = 1.0, nrm2 = 1.0;
+        i = r - 1;
+        for (; i - 3 >= 0; i -= 4) {
+            const double l0 = e[i] / A[(long long)i * ldq + j], l1 = e[i - 1] / A[(long long)(i - 1) * ldq + j],
+                         l2 = e[i - 2] / A[(long long)(i - 2) * ldq + j], l3 = e[i - 3] / A[(long long)(i - 3) * ldq + j];
+            const double z0 = -l0 * z, z1 = -l1 * z0, z2 = -l2 * z1, z3 = -l3 * z2;
+            A[(long long)i * ldq + j] = z0; A[(long long)(i - 1) * ldq + j] = z1;
+            A[(long long)(i - 2) * ldq + j] = z2; A[(long long)(i - 3) * ldq + j] = z3;
+            nrm2 += z0 * z0 + z1 * z1 + z2 * z2 + z3 * z3;
+            z = z3;
+        }
+        for (; i >= 0; --i) {
+            z = -(e[i] / A[(long long)i * ldq + j]) * z;
             A[(long long)i * ldq + j] = z;
             nrm2 = fma(z, z, nrm2);
         }
         z = 1.0;
-        for (int i = r; i < k - 1; ++i) {                  // z_{i+1} = -(e_i / D-_{i+1}) z_i
-            const double u = e[i] / B[(long long)(i + 1) * ldq + j];
-            z = -u * z;
+        i = r;
+        for (; i + 3 < k - 1; i += 4) {
+            const double u0 = e[i] / B[(long long)(i + 1) * ldq + j], u1 = e[i + 1] / B[(long long)(i + 2) * ldq + j],
+                         u2 = e[i + 2] / B[(long long)(i + 3) * ldq + j], u3 = e[i + 3] / B[(long long)(i + 4) * ldq + j];
+            const double z0 = -u0 * z, z1 = -u1 * z0, z2 = -u2 * z1, z3 = -u3 * z2;
+            A[(long long)(i + 1) * ldq + j] = z0; A[(long long)(i + 2) * ldq + j] = z1;
+            A[(long long)(i + 3) * ldq + j] = z2; A[(long long)(i + 4) * ldq + j] = z3;
+            nrm2 += z0 * z0 + z1 * z1 + z2 * z2 + z3 * z3;
+            z = z3;
+        }
+        for (; i < k - 1; ++i) {
+            z = -(e[i] / B[(long long)(i + 1) * ldq + j]) * z;
             A[(long long)(i + 1) * ldq + j] = z;
             nrm2 = fma(z, z, nrm2);
         }
         A[(long long)r * ldq + j] = 1.0;
         const double inv = rsqrt(nrm2);
         if (!(nrm2 > 0.0) || !(nrm2 < 1e300) || inv != inv) atomicExch(&bad_s, 1);
-        for (int i = 0; i < k; ++i) A[(long long)i * ldq + j] *= inv;
+        i = 0;
+        for (; i + 3 < k; i += 4) {
+            const double a0 = A[(long long)i * ldq + j], a1 = A[(long long)(i + 1) * ldq + j],
+                         a2 = A[(long long)(i + 2) * ldq + j], a3 = A[(long long)(i + 3) * ldq + j];
+            A[(long long)i * ldq + j] = a0 * inv; A[(long long)(i + 1) * ldq + j] = a1 * inv;
+            A[(long long)(i + 2) * ldq + j] = a2 * inv; A[(long long)(i + 3) * ldq + j] = a3 * inv;
+        }
+        for (; i < k; ++i) A[(long long)i * ldq + j] *= inv;
         theta[(long long)prob * thstride + j] = t0 * unsc;
     }
     __threadfence_block();
