@@ -400,9 +400,18 @@ static size_t smem_limit(const tk_handle* h) {
     return 200 * 1024;
 }
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory -- once per kernel and size, not once per launch.
 template <typename K>
 static int allow_smem(K kernel, size_t bytes) {
-    if (bytes > 48 * 1024) TK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (bytes <= 48 * 1024) return 0;
+    static std::map<std::pair<int, const void*>, size_t> granted;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t& have = granted[std::make_pair(dev, reinterpret_cast<const void*>(kernel))];
+    if (bytes > have) {
+        TK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        have = bytes;
+    }
     return 0;
 }
 
@@ -524,12 +533,31 @@ static int launch_monitor(tk_handle* h, int newcol, int base, int nmodes, int re
 }
 
 static int launch_arnoldi(tk_handle* h, int k) {
+    const double bytes = (16.0 * k + op_bytes_per_row(h) + 24.0) * (double)h->n * h->dk;
+    TimedScope ts(h, TM_MGS, bytes, h->stream);
+    KrylovParams p = h->kp();
+    const size_t hsm = (size_t)h->ncol * 8;
+    const bool reg_ok = env_int("TK_MGS_REG", 1) != 0;
+#define TK_MGS_LAUNCH(E, TH, PF)                                                      \
+    do {                                                                              \
+        arnoldi_mgs_reg_kernel<E, TH, PF><<<h->dk, TH, hsm, h->stream>>>(p, k);       \
+        h->launches++;                                                                \
+        TK_CUDA(cudaGetLastError());                                                  \
+        return 0;                                                                     \
+    } while (0)
+    if (reg_ok && hsm <= 40 * 1024) {
+        if (h->n <= 128 * 4) TK_MGS_LAUNCH(4, 128, 3);
+        if (h->n <= 256 * 4) TK_MGS_LAUNCH(4, 256, 3);
+        if (h->n <= 256 * 8) TK_MGS_LAUNCH(8, 256, 3);
+        if (h->n <= 512 * 8) TK_MGS_LAUNCH(8, 512, 3);
+        if (h->n <= 512 * 12) TK_MGS_LAUNCH(12, 512, 1);
+        if (h->n <= 1024 * 10) TK_MGS_LAUNCH(10, 1024, 0);
+    }
+#undef TK_MGS_LAUNCH
     size_t smem; double* vscr;
     TK_TRY(mgs_smem(h, &smem, &vscr));
     TK_TRY(allow_smem(arnoldi_mgs_kernel, smem));
-    const double bytes = (16.0 * k + op_bytes_per_row(h) + 24.0) * (double)h->n * h->dk;
-    TimedScope ts(h, TM_MGS, bytes, h->stream);
-    arnoldi_mgs_kernel<<<h->dk, 512, smem, h->stream>>>(h->kp(), k, vscr);
+    arnoldi_mgs_kernel<<<h->dk, 512, smem, h->stream>>>(p, k, vscr);
     h->launches++;
     TK_CUDA(cudaGetLastError());
     return 0;

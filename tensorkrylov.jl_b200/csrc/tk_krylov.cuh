@@ -246,6 +246,102 @@ __device__ void mgs_step_cta(const KrylovParams& p, int s, int k, double* v, dou
 }
 
 // ------------------------------------------------------------------------------------------
+// Register-resident Arnoldi step: same two-pass MGS in the reference's order, but the working vector lives in
+// registers (EPT rows per thread), each basis column is fetched ONCE per pass (the dot and the update use the same
+// registers), the next PD columns are already in flight while the current one is being reduced, and the block reduction
+// needs a single barrier (two alternating scratch rows).  The step is a chain of 2k dependent reductions, so the
+// latency of one reduction (~0.3 us) is what bounds it, not bandwidth.
+// ------------------------------------------------------------------------------------------
+template <int EPT, int THREADS, int PD>   // PD: basis columns kept in flight ahead of the one being reduced (0, 1 or 3)
+__global__ void __launch_bounds__(THREADS) arnoldi_mgs_reg_kernel(KrylovParams p, int k) {
+    if (*p.status != ST_RUNNING) return;
+    extern __shared__ double hcol[];                    // k+1
+    __shared__ double scr[2][32];
+    const int s = blockIdx.x, n = p.n, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = THREADS / 32;
+    constexpr int NB = PD + 1;                          // register sets for basis columns
+    const OpDesc& op = p.ops[p.mode_op[s]];
+    double* Vs = p.V + (long long)s * p.vstride;
+    const double* vk = Vs + (long long)(k - 1) * p.ldv;
+    double v[EPT], colr[NB][EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int i = tid + e * THREADS;
+        v[e] = (i < n) ? apply_row(op, vk, i, n) : 0.0;
+    }
+    int buf = 0;
+    auto reduce = [&](double x) -> double {
+        x = warp_sum(x);
+        if (lane == 0) scr[buf][warp] = x;
+        __syncthreads();
+        double r = (lane < NW) ? scr[buf][lane] : 0.0;
+        buf ^= 1;
+        return warp_sum(r);
+    };
+    for (int pass = 0; pass < 2; ++pass) {
+        // software pipeline: columns c .. c+PD are resident in registers when column c is reduced
+#pragma unroll
+        for (int q = 0; q < PD; ++q) {
+            const double* col = Vs + (long long)min(q, k - 1) * p.ldv;
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) { const int i = tid + e * THREADS; colr[q][e] = (i < n) ? col[i] : 0.0; }
+        }
+        for (int c0 = 0; c0 < k; c0 += NB) {
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                const int c = c0 + q;
+                if (c < k) {                                            // uniform across the CTA
+                    // fetch column c+PD into the set that was freed by column c-1 (or the spare set at q = 0)
+                    const int cf = c + PD;
+                    {
+                        const int slot = (q + PD) % NB;
+                        const double* col = Vs + (long long)min(cf, k - 1) * p.ldv;
+#pragma unroll
+                        for (int e = 0; e < EPT; ++e) { const int i = tid + e * THREADS; colr[slot][e] = (i < n) ? col[i] : 0.0; }
+                    }
+                    double acc = 0.0;
+#pragma unroll
+                    for (int e = 0; e < EPT; ++e) acc = fma(v[e], colr[q][e], acc);
+                    const double h = reduce(acc);
+                    if (tid == 0) hcol[c] = pass ? hcol[c] + h : h;
+#pragma unroll
+                    for (int e = 0; e < EPT; ++e) v[e] = fma(-h, colr[q][e], v[e]);
+                }
+            }
+        }
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) acc = fma(v[e], v[e], acc);
+    const double beta = sqrt(reduce(acc));
+    const double inv = 1.0 / beta;
+    double* vnew = Vs + (long long)k * p.ldv;
+    const double* b = p.b + (long long)s * p.ldv;
+    acc = 0.0;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int i = tid + e * THREADS;
+        if (i < n) {
+            const double x = v[e] * inv;
+            vnew[i] = x;
+            acc = fma(x, b[i], acc);
+        }
+    }
+    const double btn = reduce(acc);
+    __syncthreads();
+    double* Hs = p.Hd + (long long)s * p.ncol * p.ncol + (long long)(k - 1) * p.ncol;
+    for (int c = tid; c < k; c += THREADS) Hs[c] = hcol[c];
+    if (tid == 0) {
+        Hs[k] = beta;
+        p.bt[(long long)s * p.ncol + k] = btn;
+        double* T = p.T + (long long)s * 3 * p.ncol;
+        T[k - 1] = hcol[k - 1];
+        T[p.ncol + (k - 1)] = beta;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // After gram_row_kernel: fold the new Gram row into S = ||V'V - I||_F^2 and, for
 // TensorLanczosReorth, run the MGS fallback when sqrt(S) > sqrt(eps) (orthogonal_bases.jl:119-131).
 // newcol = 0-based index of the newest column (= k for step k).  One CTA per listed mode;

@@ -8,16 +8,18 @@ tk = entry.load_package()
 d = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 10000
 nmax = int(sys.argv[3]) if len(sys.argv) > 3 else 64
-variant = {"reorth": tk.TensorLanczosReorth, "lanczos": tk.TensorLanczos}[sys.argv[4] if len(sys.argv) > 4 else "reorth"]
+vname = sys.argv[4] if len(sys.argv) > 4 else "reorth"
+variant = {"reorth": tk.TensorLanczosReorth, "lanczos": tk.TensorLanczos, "arnoldi": tk.TensorArnoldi}[vname]
+inst, cls = (tk.NonSymInstance, tk.ConvDiff) if vname == "arnoldi" else (tk.SymInstance, tk.Laplace)
 per_mode = len(sys.argv) > 5 and sys.argv[5] == "1"
 flags = tk.TK_FLAG_FIXED_ITERATIONS | tk.TK_FLAG_TIME_ALL | tk.TK_FLAG_TIME_KERNELS | (0 if per_mode else tk.TK_FLAG_REFERENCE_H1)
-A1 = tk.assemble_matrix(n, tk.Laplace)
+A1 = tk.assemble_matrix(n, cls)
 b = np.random.default_rng(12345).random(n); b /= np.linalg.norm(b)
-s = tk.Solver(d, n, nmax, tk.SymInstance, tk.Laplace, variant, flags=flags)
+s = tk.Solver(d, n, nmax, inst, cls, variant, flags=flags)
 s.set_operators([A1] * d); s.set_rhs([b] * d); s.set_schedule(A1, 1e-8)
 for _ in range(3):
     r = s.solve(1e-8)
-names = ["ttr", "gram", "mgs", "eig", "assemble+gramblocks", "combine+finalize", "solve"]
+names = ["ttr", "gram", "mgs", "eig|expm", "assemble+gramblocks", "combine+finalize", "solve"]
 out = {}
 for i, nm in enumerate(names):
     ms, cnt, by = s.timing(i)
