@@ -17,6 +17,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <set>
 #include <string>
 #include <vector>
@@ -103,6 +104,7 @@ static std::map<std::string, CommEntry> g_comms;
 // ---------------------------------------------------------------------------------------------
 static std::map<std::pair<int, size_t>, std::vector<void*>> g_pool;
 static size_t g_pool_bytes = 0;
+static std::mutex g_mutex;   // guards the process-level tables (block cache, communicators, kernel attributes)
 
 static void pool_trim() {
     for (auto& kv : g_pool) {
@@ -117,6 +119,7 @@ static void pool_trim() {
 }
 
 static cudaError_t pool_alloc(void** out, size_t bytes) {
+    std::lock_guard<std::mutex> lock(g_mutex);
     int dev = 0;
     cudaGetDevice(&dev);
     auto it = g_pool.find(std::make_pair(dev, bytes));
@@ -136,6 +139,7 @@ static cudaError_t pool_alloc(void** out, size_t bytes) {
 }
 
 static void pool_free(void* q, size_t bytes) {
+    std::lock_guard<std::mutex> lock(g_mutex);
     int dev = 0;
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, q) == cudaSuccess) dev = attr.device; else cudaGetLastError();
@@ -242,6 +246,7 @@ struct tk_handle {
     DevBuf<double> exW;                 // NonSymInstance: workspace of the batched matrix exponential
     DevBuf<int> ex_nsq, ex_where, cls_mode_d;
     int ex_ld = 0;
+    int ring_depth = NBUF;              // iterations whose spectral data (theta/Q or the exponentials) may be in flight
     int ldq = 0;
     long long ystride = 0, estride = 0, pstride_max = 0;
     bool work_ready = false;
@@ -376,7 +381,10 @@ static int alloc_work(tk_handle* h) {
     if (h->world > 1) TK_TRY(h->gathered.alloc((size_t)h->world * h->nchunks * h->pstride_max));
     if (h->instance == TK_NONSYM) {
         h->ex_ld = (h->nmax + 3) & ~3;
-        const size_t nmat = (size_t)h->ncls * tmax;
+        // exponentials of up to ring_depth iterations are in flight (they only depend on the Krylov step); with one
+        // matrix class the ring is cheap, with per-mode classes it is kept at depth 1
+        h->ring_depth = h->ncls == 1 ? tk_handle::NBUF : 1;
+        const size_t nmat = (size_t)h->ncls * tmax * h->ring_depth;
         const size_t bytes = nmat * EX_SLOTS * (size_t)h->ex_ld * h->ex_ld * 8;
         size_t free_b = 0, total_b = 0;
         TK_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -405,6 +413,7 @@ template <typename K>
 static int allow_smem(K kernel, size_t bytes) {
     if (bytes <= 48 * 1024) return 0;
     static std::map<std::pair<int, const void*>, size_t> granted;
+    std::lock_guard<std::mutex> lock(g_mutex);
     int dev = 0;
     cudaGetDevice(&dev);
     size_t& have = granted[std::make_pair(dev, reinterpret_cast<const void*>(kernel))];
@@ -648,9 +657,12 @@ static CompressParams make_cp(tk_handle* h, int k) {
     return c;
 }
 
-// solve_compressed_system (tensor_krylov_method.jl:10-34), first half: the eigendecomposition(s)
+static int enqueue_expm(tk_handle* h, int k, cudaStream_t st);
+
+// solve_compressed_system (tensor_krylov_method.jl:10-34), first half: the eigendecomposition(s), or for
+// NonSymInstance the dense exponentials exp(gamma_j H)
 static int enqueue_eig(tk_handle* h, int k) {
-    if (h->instance == TK_NONSYM) return 0;   // dense exponential instead, see enqueue_expm (runs on stream2)
+    if (h->instance == TK_NONSYM) return enqueue_expm(h, k, h->stream3[k % tk_handle::NEIG]);
     // under TK_FLAG_REFERENCE_H1 the one problem is mode 1's H (this rank's own copy or its shadow copy)
     const double* Tsrc = h->per_mode ? h->T.p : h->T.p + (size_t)h->eig_slot * 3 * h->ncol;
     CompressParams c = make_cp(h, k);
@@ -664,18 +676,66 @@ static int enqueue_eig(tk_handle* h, int k) {
 }
 
 // NonSymInstance: Y_s[:,j] = exp(gamma_j H) b~_s through the batched Taylor scaling-and-squaring exponential
-static int enqueue_expm(tk_handle* h, int k) {
+static ExpmParams make_ex(tk_handle* h, int k) {
     const SchedEntry& se = h->sched[k];
+    const size_t ring = (size_t)(k % h->ring_depth), per = (size_t)h->ncls * std::max(h->tmax, 1);
     ExpmParams p;
     p.k = k; p.ld = h->ex_ld; p.t = se.t; p.ncls = h->ncls; p.ncol = h->ncol;
     p.mslot = (long long)h->ex_ld * h->ex_ld;
-    p.W = h->exW.p; p.nsq = h->ex_nsq.p; p.where = h->ex_where.p;
+    p.W = h->exW.p + ring * per * EX_SLOTS * (size_t)p.mslot;
+    p.nsq = h->ex_nsq.p + ring * per; p.where = h->ex_where.p + ring * per;
     p.Hd = h->Hd.p; p.T = h->T.p; p.cls_mode = h->cls_mode_d.p;
     p.alpha = h->alpha_d.p + se.off; p.lam_inv = 1.0 / se.lambda_min;
     p.status = h->status_d.p;
+    return p;
+}
+
+// Y_s[:, j] = E_j b~_s on the assembly stream, once the exponentials of iteration k are there
+static int enqueue_expm_apply(tk_handle* h, int k) {
+    const SchedEntry& se = h->sched[k];
+    ExpmParams p = make_ex(h, k);
+    const int tld = (se.t + 3) & ~3;
+    if (h->dl > 0) {
+        TimedScope ts(h, TM_ASM, 0.0, h->stream2);
+        expm_apply_kernel<<<dim3(h->dl, se.t), 256, (size_t)k * 8, h->stream2>>>(p, h->per_mode, h->bt.p, h->Y.p, h->ystride, tld);
+        h->launches++;
+        TK_CUDA(cudaGetLastError());
+    }
+    h->last_k = k; h->last_t = se.t; h->last_tld = tld; h->last_lam_inv = p.lam_inv;
+    return 0;
+}
+
+static int enqueue_expm(tk_handle* h, int k, cudaStream_t st) {
+    const SchedEntry& se = h->sched[k];
+    ExpmParams p = make_ex(h, k);
     const int nmat = h->ncls * se.t;
-    cudaStream_t st = h->stream2;
     TimedScope ts(h, TM_EIG, 0.0, st);
+    double f[17];
+    f[0] = 1.0;
+    for (int i = 1; i <= 16; ++i) f[i] = f[i - 1] / (double)i;    // 1/i!
+    const int tiles_f = (k + 63) / 64;
+    if (tiles_f <= 4 && !env_int("TK_EXPM_UNFUSED", 0)) {
+        // one launch: a cluster of tiles^2 CTAs per matrix walks through all products (cluster barriers in between)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)nmat * tiles_f * tiles_f);
+        cfg.blockDim = dim3(256);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = tiles_f * tiles_f; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = tiles_f > 1 ? 1 : 0;
+#define TK_EXPM_FUSED(TL)                                                                                             \
+        do {                                                                                                          \
+            if (TL * TL > 8) TK_CUDA(cudaFuncSetAttribute(expm_fused_kernel<TL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)); \
+            TK_CUDA(cudaLaunchKernelEx(&cfg, expm_fused_kernel<TL>, p, f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7], f[8],      \
+                                       f[9], f[10], f[11], f[12], f[13], f[14], f[15], f[16]));                      \
+        } while (0)
+        if (tiles_f == 1) TK_EXPM_FUSED(1); else if (tiles_f == 2) TK_EXPM_FUSED(2); else if (tiles_f == 3) TK_EXPM_FUSED(3); else TK_EXPM_FUSED(4);
+#undef TK_EXPM_FUSED
+        h->launches++;
+        return 0;
+    }
     expm_setup_kernel<<<nmat, 256, 0, st>>>(p);
     h->launches++;
     // upper bound on the squarings: ||gamma H||_1 <= |gamma| sqrt(k) ||H||_2 <= |gamma| sqrt(k) ||A||_2
@@ -693,9 +753,6 @@ static int enqueue_expm(tk_handle* h, int k) {
         expm_gemm_kernel<<<grid, 256, 0, st>>>(p, job);
         h->launches++;
     };
-    double f[17];
-    f[0] = 1.0;
-    for (int i = 1; i <= 16; ++i) f[i] = f[i - 1] / (double)i;    // 1/i!
     gemm(0, 0, 1, 0, 0, 0, 0, 0, 0, -1);     // A2 = A A
     gemm(1, 0, 2, 0, 0, 0, 0, 0, 0, -1);     // A3 = A2 A
     gemm(1, 1, 3, 0, 0, 0, 0, 0, 0, -1);     // A4 = A2 A2
@@ -706,19 +763,12 @@ static int enqueue_expm(tk_handle* h, int k) {
     gemm(3, 5, 4, 1, f[0], f[1], f[2], f[3], 0.0, -1);
     for (int sq = 0; sq < smax; ++sq) gemm(0, 0, 0, 0, 0, 0, 0, 0, 0, sq);
     TK_CUDA(cudaGetLastError());
-    const int tld = (se.t + 3) & ~3;
-    if (h->dl > 0) {
-        expm_apply_kernel<<<dim3(h->dl, se.t), 256, (size_t)k * 8, st>>>(p, h->per_mode, h->bt.p, h->Y.p, h->ystride, tld);
-        h->launches++;
-        TK_CUDA(cudaGetLastError());
-    }
-    h->last_k = k; h->last_t = se.t; h->last_tld = tld; h->last_lam_inv = p.lam_inv;
     return 0;
 }
 
 // second half: CP assembly of Y_s for every local mode
 static int enqueue_assemble(tk_handle* h, int k) {
-    if (h->instance == TK_NONSYM) return enqueue_expm(h, k);
+    if (h->instance == TK_NONSYM) return enqueue_expm_apply(h, k);
     CompressParams c = make_cp(h, k);
     const size_t smem = ((size_t)2 * k + (size_t)k * ASM_TJ) * 8;
     TK_TRY(allow_smem(assemble_cp_kernel, smem));
@@ -950,6 +1000,7 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
     if (world > 1) {
         TK_TRY(nccl_bind());
         const std::string key(static_cast<const char*>(unique_id), 128);
+        std::lock_guard<std::mutex> lock(g_mutex);
         auto it = g_comms.find(key);
         if (it == g_comms.end()) {
             ncclUniqueId id;
@@ -992,6 +1043,7 @@ void tk_destroy(tk_handle* h) {
 }
 
 int tk_release_cache(void) {
+    std::lock_guard<std::mutex> lock(g_mutex);
     pool_trim();
     return 0;
 }
@@ -1277,7 +1329,7 @@ int tk_solve(tk_handle* h, double tol, int32_t* status, int64_t* niter, int32_t*
         // eigensolver stream: needs step k; its (theta, Q) buffer k&1 was last read by the assembly of k-2
         cudaStream_t es = h->stream3[k % tk_handle::NEIG];
         TK_CUDA(cudaStreamWaitEvent(es, h->step_ev[slot], 0));
-        if (k - tk_handle::NBUF >= 2) TK_CUDA(cudaStreamWaitEvent(es, h->asm_ev[(k - tk_handle::NBUF) % RING], 0));
+        if (k - h->ring_depth >= 2) TK_CUDA(cudaStreamWaitEvent(es, h->asm_ev[(k - h->ring_depth) % RING], 0));
         TK_TRY(enqueue_eig(h, k));
         TK_CUDA(cudaEventRecord(h->eig_ev[slot], es));
         // assembly + residual stream

@@ -83,23 +83,12 @@ struct GemmJob {
                               //       slot 4 + (sq_step & 1), writes slot 4 + ((sq_step + 1) & 1)
 };
 
-__global__ void __launch_bounds__(256) expm_gemm_kernel(ExpmParams p, GemmJob job) {
-    if (*p.status != ST_RUNNING) return;
-    const int m = blockIdx.z, k = p.k, ld = p.ld;
-    int sa = job.a, sb = job.b, sc = job.c;
-    if (job.sq_step >= 0) {
-        if (p.nsq[m] <= job.sq_step) return;
-        sa = sb = 4 + (job.sq_step & 1);
-        sc = 4 + ((job.sq_step + 1) & 1);
-    }
-    double* rec = p.W + (long long)m * EX_SLOTS * p.mslot;
-    const double* A = rec + (long long)sa * p.mslot;
-    const double* B = rec + (long long)sb * p.mslot;
-    double* C = rec + (long long)sc * p.mslot;
-    __shared__ double As[16][64 + 1];
-    __shared__ double Bs[16][64 + 1];
+// One 64x64 tile of C = A*B (+ Taylor block), 256 threads, 4x4 outputs per thread, K step 16 through shared memory.
+__device__ __forceinline__ void gemm_tile(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
+                                          const double* rec, long long mslot, int k, int ld, int row0, int col0, int comb,
+                                          double c0, double c1, double c2, double c3, double c4, double (*As)[65],
+                                          double (*Bs)[65]) {
     const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;   // 16 x 16 threads, each 4 x 4 outputs
-    const int row0 = blockIdx.y * 64, col0 = blockIdx.x * 64;
     double acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -110,13 +99,13 @@ __global__ void __launch_bounds__(256) expm_gemm_kernel(ExpmParams p, GemmJob jo
         for (int idx = threadIdx.x; idx < 64 * 16; idx += 256) {
             const int r = idx % 64, cc = idx / 64;
             const int gr = row0 + r, gc = kk + cc;
-            As[cc][r] = (gr < k && gc < k) ? A[(long long)gc * ld + gr] : 0.0;
+            As[cc][r] = (gr < k && gc < k) ? __ldcg(A + (long long)gc * ld + gr) : 0.0;
         }
         // B tile: rows kk..kk+15, cols col0..col0+63
         for (int idx = threadIdx.x; idx < 16 * 64; idx += 256) {
             const int r = idx % 16, cc = idx / 16;
             const int gr = kk + r, gc = col0 + cc;
-            Bs[r][cc] = (gr < k && gc < k) ? B[(long long)gc * ld + gr] : 0.0;
+            Bs[r][cc] = (gr < k && gc < k) ? __ldcg(B + (long long)gc * ld + gr) : 0.0;
         }
         __syncthreads();
 #pragma unroll
@@ -133,10 +122,10 @@ __global__ void __launch_bounds__(256) expm_gemm_kernel(ExpmParams p, GemmJob jo
         }
         __syncthreads();
     }
-    const double* X1 = rec;                       // A
-    const double* X2 = rec + 1 * p.mslot;         // A2
-    const double* X3 = rec + 2 * p.mslot;         // A3
-    const double* X4 = rec + 3 * p.mslot;         // A4
+    const double* X1 = rec;                     // A
+    const double* X2 = rec + 1 * mslot;         // A2
+    const double* X3 = rec + 2 * mslot;         // A3
+    const double* X4 = rec + 3 * mslot;         // A4
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -145,14 +134,107 @@ __global__ void __launch_bounds__(256) expm_gemm_kernel(ExpmParams p, GemmJob jo
             if (gr < k && gc < k) {
                 const long long off = (long long)gc * ld + gr;
                 double v = acc[i][jj];
-                if (job.comb) {
-                    v += job.c1 * X1[off] + job.c2 * X2[off] + job.c3 * X3[off];
-                    if (job.c4 != 0.0) v += job.c4 * X4[off];
-                    if (gr == gc) v += job.c0;
+                if (comb) {
+                    v += c1 * X1[off] + c2 * X2[off] + c3 * X3[off];
+                    if (c4 != 0.0) v += c4 * X4[off];
+                    if (gr == gc) v += c0;
                 }
                 C[off] = v;
             }
         }
+}
+
+__global__ void __launch_bounds__(256) expm_gemm_kernel(ExpmParams p, GemmJob job) {
+    if (*p.status != ST_RUNNING) return;
+    const int m = blockIdx.z;
+    int sa = job.a, sb = job.b, sc = job.c;
+    if (job.sq_step >= 0) {
+        if (p.nsq[m] <= job.sq_step) return;
+        sa = sb = 4 + (job.sq_step & 1);
+        sc = 4 + ((job.sq_step + 1) & 1);
+    }
+    double* rec = p.W + (long long)m * EX_SLOTS * p.mslot;
+    __shared__ double As[16][65];
+    __shared__ double Bs[16][65];
+    gemm_tile(rec + (long long)sa * p.mslot, rec + (long long)sb * p.mslot, rec + (long long)sc * p.mslot, rec, p.mslot, p.k,
+              p.ld, blockIdx.y * 64, blockIdx.x * 64, job.comb, job.c0, job.c1, job.c2, job.c3, job.c4, As, Bs);
+}
+
+// ------------------------------------------------------------------------------------------
+// The whole exponential of one matrix in ONE launch: a thread-block cluster of TILES x TILES CTAs per matrix, CTA
+// (ty, tx) owns the 64 x 64 tile (ty, tx) of every product; the products are separated by cluster barriers (the
+// operands live in global memory / L2).  Every matrix does exactly its own number of squarings.  Replaces ~7 + s
+// dependent tiny launches per iteration; k <= 64*TILES, cluster sizes 1, 4, 9 and 16 (the last two non-portable).
+// ------------------------------------------------------------------------------------------
+template <int TILES>
+__global__ void __launch_bounds__(256) expm_fused_kernel(ExpmParams p, double f0, double f1, double f2, double f3,
+                                                         double f4, double f5, double f6, double f7, double f8, double f9,
+                                                         double f10, double f11, double f12, double f13, double f14,
+                                                         double f15, double f16) {
+    if (*p.status != ST_RUNNING) return;
+    __shared__ double As[16][65];
+    __shared__ double Bs[16][65];
+    __shared__ double scratch[32];
+    constexpr int CL = TILES * TILES;
+    const int m = blockIdx.x / CL, ct = blockIdx.x % CL;
+    const int row0 = (ct / TILES) * 64, col0 = (ct % TILES) * 64;
+    const int c = m / p.t, j = m % p.t, k = p.k, ld = p.ld;
+    const int slot = p.cls_mode[c];
+    double* rec = p.W + (long long)m * EX_SLOTS * p.mslot;
+    auto csync = [&]() {
+        __threadfence();
+        if (CL > 1) cg::this_cluster().sync(); else __syncthreads();
+    };
+    // ---- scaling: every CTA computes the 1-norm (k^2 cached reads), then writes its own tile of A
+    const double gamma = -p.alpha[j] * p.lam_inv;
+    double best = 0.0;
+    for (int col = 0; col < k; ++col) {
+        double acc = 0.0;
+        for (int r = threadIdx.x; r < k; r += blockDim.x) acc += fabs(hess_entry(p, slot, r, col));
+        acc = block_sum(acc, scratch);
+        best = fmax(best, acc);
+    }
+    const double nrm = fabs(gamma) * best;
+    int s = 0;
+    if (nrm > EX_THETA) s = max((int)ceil(log2(nrm / EX_THETA)), 0);
+    const double scale = gamma * exp2((double)-s);
+    for (int idx = threadIdx.x; idx < 64 * 64; idx += blockDim.x) {
+        const int r = row0 + idx % 64, col = col0 + idx / 64;
+        if (r < ld && col < ld) rec[(long long)col * ld + r] = (r < k && col < k) ? scale * hess_entry(p, slot, r, col) : 0.0;
+    }
+    if (ct == 0 && threadIdx.x == 0) { p.nsq[m] = s; p.where[m] = 4 + (s & 1); }
+    csync();
+    auto G = [&](int a, int b, int cdst, int comb, double c0, double c1, double c2, double c3, double c4) {
+        gemm_tile(rec + (long long)a * p.mslot, rec + (long long)b * p.mslot, rec + (long long)cdst * p.mslot, rec, p.mslot,
+                  k, ld, row0, col0, comb, c0, c1, c2, c3, c4, As, Bs);
+    };
+    G(0, 0, 1, 0, 0, 0, 0, 0, 0);                 // A2
+    csync();
+    G(1, 0, 2, 0, 0, 0, 0, 0, 0);                 // A3
+    G(1, 1, 3, 0, 0, 0, 0, 0, 0);                 // A4
+    csync();
+    // top of the Horner scheme: slot 5 <- f12 I + f13 A + f14 A2 + f15 A3 + f16 A4 (own tile only)
+    for (int idx = threadIdx.x; idx < 64 * 64; idx += blockDim.x) {
+        const int r = row0 + idx % 64, col = col0 + idx / 64;
+        if (r < k && col < k) {
+            const long long off = (long long)col * ld + r;
+            double v = f13 * rec[off] + f14 * rec[p.mslot + off] + f15 * rec[2 * p.mslot + off] + f16 * rec[3 * p.mslot + off];
+            if (r == col) v += f12;
+            rec[5 * p.mslot + off] = v;
+        }
+    }
+    csync();
+    G(3, 5, 4, 1, f8, f9, f10, f11, 0.0);
+    csync();
+    G(3, 4, 5, 1, f4, f5, f6, f7, 0.0);
+    csync();
+    G(3, 5, 4, 1, f0, f1, f2, f3, 0.0);
+    csync();
+    for (int sq = 0; sq < s; ++sq) {
+        const int src = 4 + (sq & 1), dst = 4 + ((sq + 1) & 1);
+        G(src, src, dst, 0, 0, 0, 0, 0, 0);
+        csync();
+    }
 }
 
 // slot 5 <- c12 I + c13 A + c14 A2 + c15 A3 + c16 A4   (start of the Horner scheme in A4; the three Horner products

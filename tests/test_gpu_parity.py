@@ -358,6 +358,43 @@ def test_nonsym_compress_and_residual_phases(tk, orc, gpu, d, n, nmax, per_mode)
     slv.close()
 
 
+def test_nonsym_exponential_large_k(tk, orc, gpu):
+    """The cluster-fused exponential at k > 64 and k > 128 (clusters of 4 and 9 CTAs per matrix) and, with
+    TK_EXPM_UNFUSED, the plain batched-GEMM path: Y = exp(gamma_j H) b~ against the oracle's Pade expm."""
+    import os
+    d, n, nmax = 2, 200, 134
+    rng = np.random.default_rng(3)
+    one = rng.random(n)
+    b = orc.normalize_rhs([one] * d)
+    A = tk.assemble_matrix(n, tk.ConvDiff)
+    Ao = orc.assemble_matrix(n, orc.CONVDIFF)
+    S = orc.OracleSolve([Ao] * d, b, 1e-6, nmax, orc.ARNOLDI, orc.NONSYM, orc.CONVDIFF, None)
+    slv = make_solver(tk, [A] * d, b, nmax, tk.TensorArnoldi, tk.NonSymInstance, tk.ConvDiff, tol=1e-6)
+    slv.begin()
+    checks = {40: False, 66: False, 130: False, 134: True}
+    for k in range(2, nmax + 1):
+        slv.step_bases(k)
+        for s in range(d):
+            S._step(s, k)
+            S.bt[s][k - 1] = S.V[s][:, k - 1] @ S.b[s]
+        if k in checks:
+            sc = S.schedule[k]
+            Hk = [S.H[s][:k, :k] for s in range(d)]
+            btk = [S.bt[s][:k] for s in range(d)]
+            _, Yo = orc.solve_compressed_system(Hk, btk, sc["alpha"], sc["omega"], sc["lambda_min"], orc.NONSYM,
+                                                orc.CONVDIFF)
+            if checks[k]:
+                os.environ["TK_EXPM_UNFUSED"] = "1"
+            try:
+                slv.compress(k)
+            finally:
+                os.environ.pop("TK_EXPM_UNFUSED", None)
+            Y = slv.get_Y(1, k)
+            assert Y.shape == Yo[1].shape
+            assert rel(Y, Yo[1]) < 1e-9, f"k={k}"
+    slv.close()
+
+
 def test_sym_instance_with_arnoldi_basis(tk, orc, tables, gpu):
     """TensorArnoldi on a SymInstance system: the compressed solve reads Symmetric(H_1, :L) of the Hessenberg matrix
     (tensor_struct.jl:259) while Z = H Y uses the full H (utils.jl:247)."""
