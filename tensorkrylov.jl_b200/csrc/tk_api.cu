@@ -243,6 +243,8 @@ struct tk_handle {
     DevBuf<double> theta, Q, Y, Z, E, bbm, partials, gathered, bnorm_d, relres_d, projres_d, orth_d, detail_d;
     DevBuf<double> eig_scratch;         // second k x k plane per eigenproblem (bisection kernel), same ring as Q
     DevBuf<int> eig_need;               // per problem: 1 if the QL fallback must recompute it
+    DevBuf<unsigned int> ticket_d;      // last-CTA-done counter of combine_chunk_kernel
+    DevBuf<double> merged;              // this GPU's merged partial (what the all-gather ships)
     DevBuf<double> exW;                 // NonSymInstance: workspace of the batched matrix exponential
     DevBuf<int> ex_nsq, ex_where, cls_mode_d;
     int ex_ld = 0;
@@ -378,7 +380,9 @@ static int alloc_work(tk_handle* h) {
     TK_TRY(h->bbm.alloc(h->dl));
     h->pstride_max = 5LL * tmax * tmax + 2LL * tmax + 8;
     TK_TRY(h->partials.alloc((size_t)h->nchunks * h->pstride_max));
-    if (h->world > 1) TK_TRY(h->gathered.alloc((size_t)h->world * h->nchunks * h->pstride_max));
+    TK_TRY(h->ticket_d.alloc(1));
+    TK_TRY(h->merged.alloc((size_t)h->pstride_max));
+    if (h->world > 1) TK_TRY(h->gathered.alloc((size_t)h->world * h->pstride_max));
     if (h->instance == TK_NONSYM) {
         h->ex_ld = (h->nmax + 3) & ~3;
         // exponentials of up to ring_depth iterations are in flight (they only depend on the Krylov step); with one
@@ -794,15 +798,16 @@ static int enqueue_residual(tk_handle* h, int k, double tol) {
     const long long pst = 5LL * c.t * c.t + 2LL * c.t + 8;
     TimedScope ts(h, TM_COMBINE, 0.0, h->stream2);
     combine_chunk_kernel<<<h->nchunks, 256, 0, h->stream2>>>(c, h->dl, h->chunk_modes, h->chunk_base, h->partials.p, pst,
-                                                            h->orthS.p, (h->first == 0 && h->dl > 0) ? 0 : -1);
+                                                            h->orthS.p, (h->first == 0 && h->dl > 0) ? 0 : -1, h->ticket_d.p,
+                                                            h->merged.p);
     h->launches++;
     TK_CUDA(cudaGetLastError());
-    const double* parts = h->partials.p;
-    int nparts = h->nchunks;
+    const double* parts = h->merged.p;
+    int nparts = 1;
     if (h->world > 1) {
-        TK_NCCL(g_nccl.AllGather(h->partials.p, h->gathered.p, (size_t)h->nchunks * pst, ncclDouble, h->comm, h->stream2));
+        TK_NCCL(g_nccl.AllGather(h->merged.p, h->gathered.p, (size_t)pst, ncclDouble, h->comm, h->stream2));
         parts = h->gathered.p;
-        nparts = h->nchunks * h->world;
+        nparts = h->world;
     }
     FinalizeParams f;
     f.k = k; f.t = c.t; f.nmax = h->nmax; f.nparts = nparts;

@@ -522,10 +522,14 @@ __global__ void __launch_bounds__(256) gram_blocks_kernel(CompressParams p) {
 // modes -> one partial, and partials merge across chunks and across GPUs.
 // partial layout: P0 | Pe | Ph | Peh | Pg (t*t each) | v0 | v1 (t each) | bb | orthS | ...
 // ------------------------------------------------------------------------------------------
+// The CTA that finishes last (ticket counter) merges this GPU's chunk partials, in chunk order, into ONE partial:
+// that is what crosses NVLink (18 KB per GPU at t = 21 instead of one partial per chunk) and what finalize_kernel
+// merges across GPUs.
 __global__ void __launch_bounds__(256) combine_chunk_kernel(CompressParams p, int dl, int chunk_modes, int chunk_base,
                                                             double* partials, long long pstride, const double* orthS,
-                                                            int mode0_local) {
+                                                            int mode0_local, unsigned int* ticket, double* merged) {
     if (*p.status != ST_RUNNING) return;
+    __shared__ unsigned int my_ticket;
     const int t = p.t, tt = t * t, k = p.k, tld = p.tld;
     const int q0 = blockIdx.x * chunk_modes - chunk_base, q1 = min(dl, q0 + chunk_modes);
     const int qb = max(q0, 0);
@@ -562,6 +566,51 @@ __global__ void __launch_bounds__(256) combine_chunk_kernel(CompressParams p, in
         for (int q = qb; q < q1; ++q) bb *= p.bb[q];
         P[5 * tt + 2 * t] = bb;
         P[5 * tt + 2 * t + 1] = (mode0_local >= qb && mode0_local < q1) ? orthS[k - 1] : -1.0;
+    }
+    // ---- last CTA: ordered merge of all chunk partials of this GPU
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) my_ticket = atomicAdd(ticket, 1u);
+    __syncthreads();
+    if (my_ticket != gridDim.x - 1) return;
+    __threadfence();
+    const int nparts = gridDim.x;
+    for (int pidx = threadIdx.x; pidx < tt; pidx += blockDim.x) {
+        double P0 = 1.0, Pe = 0.0, Ph = 0.0, Peh = 0.0, Pg = 0.0;
+        for (int c = 0; c < nparts; ++c) {
+            const double* B = partials + (long long)c * pstride;
+            const double B0 = __ldcg(B + pidx), Be = __ldcg(B + tt + pidx), Bh = __ldcg(B + 2 * tt + pidx),
+                         Beh = __ldcg(B + 3 * tt + pidx), Bg = __ldcg(B + 4 * tt + pidx);
+            Peh = fma(Peh, B0, fma(Pe, Bh, fma(Ph, Be, P0 * Beh)));
+            Pe = fma(Pe, B0, P0 * Be);
+            Ph = fma(Ph, B0, P0 * Bh);
+            Pg = fma(Pg, B0, P0 * Bg);
+            P0 *= B0;
+        }
+        merged[pidx] = P0; merged[tt + pidx] = Pe; merged[2 * tt + pidx] = Ph; merged[3 * tt + pidx] = Peh; merged[4 * tt + pidx] = Pg;
+    }
+    for (int i = threadIdx.x; i < t; i += blockDim.x) {
+        double v0 = 1.0, v1 = 0.0;
+        for (int c = 0; c < nparts; ++c) {
+            const double* B = partials + (long long)c * pstride + 5 * tt;
+            const double b0 = __ldcg(B + i), b1 = __ldcg(B + t + i);
+            v1 = fma(v1, b0, v0 * b1);
+            v0 *= b0;
+        }
+        merged[5 * tt + i] = v0;
+        merged[5 * tt + t + i] = v1;
+    }
+    if (threadIdx.x == 0) {
+        double bb = 1.0, oS = -1.0;
+        for (int c = 0; c < nparts; ++c) {
+            const double* B = partials + (long long)c * pstride + 5 * tt + 2 * t;
+            bb *= __ldcg(B);
+            const double o = __ldcg(B + 1);
+            if (o >= 0.0) oS = o;
+        }
+        merged[5 * tt + 2 * t] = bb;
+        merged[5 * tt + 2 * t + 1] = oS;
+        *ticket = 0u;
     }
 }
 
