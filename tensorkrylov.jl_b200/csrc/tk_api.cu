@@ -244,6 +244,7 @@ struct tk_handle {
     DevBuf<double> eig_scratch;         // second k x k plane per eigenproblem (bisection kernel), same ring as Q
     DevBuf<int> eig_need;               // per problem: 1 if the QL fallback must recompute it
     DevBuf<unsigned int> ticket_d;      // last-CTA-done counter of combine_chunk_kernel
+    DevBuf<unsigned int> tickets;       // per mode: last-CTA-done counter of gram_row_kernel
     DevBuf<double> merged;              // this GPU's merged partial (what the all-gather ships)
     DevBuf<double> exW;                 // NonSymInstance: workspace of the batched matrix exponential
     DevBuf<int> ex_nsq, ex_where, cls_mode_d;
@@ -484,7 +485,9 @@ static int launch_ttr(tk_handle* h, int k) {
 }
 
 // Gram row of the newest column for `nmodes` modes starting at local mode `base`
-static int launch_gram(tk_handle* h, int ncols, int base, int nmodes) {
+// Gram row of the newest column for `nmodes` modes starting at local mode `base`, followed (same launch, last CTA of
+// each mode) by the monitor: monitor = 0 plain bookkeeping, 1 = with the LanczosReorth MGS fallback.
+static int launch_gram(tk_handle* h, int ncols, int base, int nmodes, int monitor) {
     if (nmodes <= 0) return 0;
     const int threads = env_int("TK_GRAM_THREADS", 256) == 512 ? 512 : 256, nwarp = threads / 32;
     // warps per column: long columns are cut into segments so all warps of a CTA stream the same amount
@@ -493,15 +496,27 @@ static int launch_gram(tk_handle* h, int ncols, int base, int nmodes) {
     wpc = std::min(wpc, nwarp);
     const int maxcpc = env_int("TK_GRAM_CPC", 32);
     const int gran = nwarp / wpc;                    // columns a CTA processes per pass
-    // <= maxcpc columns per CTA (the new vector is re-staged once per CTA); more chunks when there are few modes
-    int nchunks = (ncols + maxcpc - 1) / maxcpc;
-    const long long want = (592 + nmodes - 1) / nmodes;
-    nchunks = (int)std::max<long long>(nchunks, std::min<long long>(want, (ncols + gran - 1) / gran));
+    // chunks per mode: at most maxcpc columns per CTA (the new vector is re-staged once per CTA); among the
+    // admissible counts pick the one whose grid fills whole waves of 2 CTAs x 148 SMs best
+    const int lo_ch = (ncols + maxcpc - 1) / maxcpc, hi_ch = std::max(lo_ch, std::min((ncols + gran - 1) / gran, 48));
+    int nchunks = lo_ch;
+    double best = -1.0;
+    for (int c = lo_ch; c <= hi_ch; ++c) {
+        const double ctas = (double)c * nmodes, waves = std::ceil(ctas / 296.0);
+        const int cpc_c = (ncols + c - 1) / c;
+        const double score = ctas / (waves * 296.0) / (1.0 + 1.0 / cpc_c);
+        if (score > best + 1e-9) { best = score; nchunks = c; }
+    }
+    if (env_int("TK_GRAM_CHUNKS", 0)) nchunks = env_int("TK_GRAM_CHUNKS", 0);
     int cpc = (ncols + nchunks - 1) / nchunks;
     nchunks = (ncols + cpc - 1) / cpc;
-    size_t smem = (size_t)cpc * GRAM_PSTRIDE * 8 + (size_t)h->n * 8;
+    const size_t fixed = ((size_t)cpc * GRAM_PSTRIDE + ((h->ncol + 1) & ~1)) * 8;
+    size_t smem = fixed + (size_t)h->n * 8;
     const bool w_smem = smem <= smem_limit(h);
-    if (!w_smem) smem = (size_t)cpc * GRAM_PSTRIDE * 8;
+    if (!w_smem) {
+        smem = fixed;
+        if (monitor > 0 && !h->vscratch.p) TK_TRY(h->vscratch.alloc((size_t)h->dk * h->ldv));
+    }
     const double bytes = 8.0 * (double)h->n * (double)ncols * nmodes;
     const int U = env_int("TK_GRAM_U", 4);
     TimedScope ts(h, TM_GRAM, bytes, h->stream);
@@ -509,7 +524,8 @@ static int launch_gram(tk_handle* h, int ncols, int base, int nmodes) {
     do {                                                                                                         \
         TK_TRY(allow_smem(gram_row_kernel<UU, TT>, smem));                                                       \
         gram_row_kernel<UU, TT><<<dim3(nchunks, nmodes), TT, smem, h->stream>>>(h->kp(), ncols, cpc, base,       \
-                                                                                w_smem ? 1 : 0, wpc);            \
+                                                                                w_smem ? 1 : 0, wpc, monitor,    \
+                                                                                h->tickets.p, h->vscratch.p);    \
     } while (0)
     if (threads == 512) {
         if (U == 8) TK_GRAM_LAUNCH(8, 512); else if (U == 2) TK_GRAM_LAUNCH(2, 512); else TK_GRAM_LAUNCH(4, 512);
@@ -530,18 +546,6 @@ static int mgs_smem(tk_handle* h, size_t* smem, double** vscr) {
         if (!h->vscratch.p) TK_TRY(h->vscratch.alloc((size_t)h->dk * h->ldv));
         *smem = (size_t)h->ncol * 8; *vscr = h->vscratch.p;
     }
-    return 0;
-}
-
-static int launch_monitor(tk_handle* h, int newcol, int base, int nmodes, int reorth) {
-    if (nmodes <= 0) return 0;
-    size_t smem; double* vscr;
-    TK_TRY(mgs_smem(h, &smem, &vscr));
-    if (!reorth) { smem = 0; }
-    TK_TRY(allow_smem(monitor_kernel, smem));
-    monitor_kernel<<<nmodes, 512, smem, h->stream>>>(h->kp(), newcol, base, reorth, vscr);
-    h->launches++;
-    TK_CUDA(cudaGetLastError());
     return 0;
 }
 
@@ -581,16 +585,13 @@ static int enqueue_step_bases(tk_handle* h, int k) {
     const int mode0 = (h->first == 0 && h->dl > 0) ? 1 : 0;
     if (h->variant == TK_ARNOLDI) {
         TK_TRY(launch_arnoldi(h, k));
-        TK_TRY(launch_gram(h, k + 1, 0, mode0));
-        TK_TRY(launch_monitor(h, k, 0, mode0, 0));
+        TK_TRY(launch_gram(h, k + 1, 0, mode0, 0));
     } else {
         TK_TRY(launch_ttr(h, k));
         if (h->variant == TK_LANCZOS_REORTH) {
-            TK_TRY(launch_gram(h, k + 1, 0, h->dk));
-            TK_TRY(launch_monitor(h, k, 0, h->dk, 1));
+            TK_TRY(launch_gram(h, k + 1, 0, h->dk, 1));
         } else {
-            TK_TRY(launch_gram(h, k + 1, 0, mode0));
-            TK_TRY(launch_monitor(h, k, 0, mode0, 0));
+            TK_TRY(launch_gram(h, k + 1, 0, mode0, 0));
         }
     }
     return 0;
@@ -778,7 +779,7 @@ static int enqueue_assemble(tk_handle* h, int k) {
     TK_TRY(allow_smem(assemble_cp_kernel, smem));
     if (h->dl > 0) {
         TimedScope ts(h, TM_ASM, 0.0, h->stream2);
-        assemble_cp_kernel<<<h->dl, 256, smem, h->stream2>>>(c);
+        assemble_cp_kernel<<<h->dl, 256, smem, h->stream2>>>(c);     // also forms Z and the Gram blocks of the mode
         h->launches++;
         TK_CUDA(cudaGetLastError());
     }
@@ -789,7 +790,7 @@ static int enqueue_assemble(tk_handle* h, int k) {
 // residualnorm! (utils.jl:402-443) + exits of the loop body (tensor_krylov_method.jl:85-118)
 static int enqueue_residual(tk_handle* h, int k, double tol) {
     CompressParams c = make_cp(h, k);
-    if (h->dl > 0) {
+    if (h->dl > 0 && h->instance == TK_NONSYM) {      // the symmetric path did this inside assemble_cp_kernel
         TimedScope ts(h, TM_ASM, 0.0, h->stream2);
         gram_blocks_kernel<<<h->dl, 256, 0, h->stream2>>>(c);
         h->launches++;
@@ -880,8 +881,7 @@ static int begin_solve(tk_handle* h) {
     // Gram "row" of column 1 starts the orthogonality bookkeeping, then step k = 1
     const int mode0 = (h->first == 0 && h->dl > 0) ? 1 : 0;
     const int nmon = h->variant == TK_LANCZOS_REORTH ? h->dk : mode0;
-    TK_TRY(launch_gram(h, 1, 0, nmon));
-    TK_TRY(launch_monitor(h, 0, 0, nmon, 0));
+    TK_TRY(launch_gram(h, 1, 0, nmon, 0));
     TK_TRY(enqueue_step_bases(h, 1));
     h->begun = true;
     return 0;
@@ -986,6 +986,7 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
     TK_TRY(h->orthS.alloc(h->ncol));
     TK_TRY(h->bnorm2.alloc(dl));
     TK_TRY(h->fallbacks.alloc(dl));
+    TK_TRY(h->tickets.alloc(dl));
     TK_TRY(h->mode_op_d.alloc(dl));
     TK_TRY(h->status_d.alloc(1));
     TK_TRY(h->term_k_d.alloc(1));

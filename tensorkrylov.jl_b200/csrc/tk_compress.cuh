@@ -406,6 +406,8 @@ struct CompressParams {
 // ------------------------------------------------------------------------------------------
 constexpr int ASM_TJ = 16;
 
+__device__ void gram_blocks_body(const CompressParams& p, double* scratch);
+
 __global__ void __launch_bounds__(256) assemble_cp_kernel(CompressParams p) {
     if (*p.status != ST_RUNNING) return;
     extern __shared__ double smem[];
@@ -456,6 +458,9 @@ __global__ void __launch_bounds__(256) assemble_cp_kernel(CompressParams p) {
         }
         __syncthreads();
     }
+    // same CTA, same mode: Z_s = H_s Y_s and the Gram blocks (kernel (4a)) while Y_s is still hot in L1/L2
+    __shared__ double scratch_g[32];
+    gram_blocks_body(p, scratch_g);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -463,9 +468,7 @@ __global__ void __launch_bounds__(256) assemble_cp_kernel(CompressParams p) {
 // Symmetric wrapper (utils.jl:247), so the un-symmetric entry H[k-1,k] left by an MGS fallback
 // is honoured through T[2].
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gram_blocks_kernel(CompressParams p) {
-    if (*p.status != ST_RUNNING) return;
-    __shared__ double scratch[32];
+__device__ void gram_blocks_body(const CompressParams& p, double* scratch) {
     const int s = blockIdx.x, k = p.k, t = p.t, tld = p.tld;
     const double* Y = p.Y + (long long)s * p.ystride;
     double* Z = p.Z + (long long)s * p.ystride;
@@ -510,6 +513,12 @@ __global__ void __launch_bounds__(256) gram_blocks_kernel(CompressParams p) {
     for (int r = threadIdx.x; r < k; r += blockDim.x) acc = fma(bt[r], bt[r], acc);
     acc = block_sum(acc, scratch);
     if (threadIdx.x == 0) p.bb[s] = acc;
+}
+
+__global__ void __launch_bounds__(256) gram_blocks_kernel(CompressParams p) {
+    if (*p.status != ST_RUNNING) return;
+    __shared__ double scratch[32];
+    gram_blocks_body(p, scratch);
 }
 
 // ------------------------------------------------------------------------------------------

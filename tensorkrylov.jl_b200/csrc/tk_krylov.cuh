@@ -3,7 +3,7 @@
 //   init_basis_kernel     V[:,1] = b/||b||, b~[1]                (decompositions.jl:112-118, utils.jl:456-464)
 //   lanczos_ttr_kernel    3-term recurrence step                (orthogonal_bases.jl:39-67)
 //   gram_row_kernel       g_j = v_j . v_{k+1}, j = 1..k+1       (the only NEW row of V'V; orthogonal_bases.jl:119,250-257)
-//   monitor_kernel        loss test + MGS fallback              (orthogonal_bases.jl:119-131)
+//   monitor_body          loss test + MGS fallback, run by the last gram_row CTA of a mode (orthogonal_bases.jl:119-131)
 //   arnoldi_mgs_kernel    two-pass modified Gram-Schmidt step   (orthogonal_bases.jl:15-37)
 #pragma once
 #include "tk_device.cuh"
@@ -110,6 +110,93 @@ __global__ void __launch_bounds__(512) lanczos_ttr_kernel(KrylovParams p, int k)
 }
 
 // ------------------------------------------------------------------------------------------
+// CTA-wide modified Gram-Schmidt step k (orthogonal_bases.jl:15-37) for mode s.
+// v: working vector of n doubles (shared or global scratch); every thread owns the rows
+// i = tid, tid + blockDim, ... so the dot/axpy sequence needs no barrier besides the reduction.
+// hcol[0..k-1] = H[1:k,k], hcol[k] = H[k+1,k].  Writes V[:,k+1] and b~[k+1].
+// ------------------------------------------------------------------------------------------
+__device__ void mgs_step_cta(const KrylovParams& p, int s, int k, double* v, double* hcol, double* scratch) {
+    const int n = p.n;
+    const OpDesc& op = p.ops[p.mode_op[s]];
+    double* Vs = p.V + (long long)s * p.vstride;
+    const double* vk = Vs + (long long)(k - 1) * p.ldv;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v[i] = apply_row(op, vk, i, n);
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int c = 0; c < k; ++c) {
+            const double* col = Vs + (long long)c * p.ldv;
+            double acc = 0.0;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) acc = fma(v[i], col[i], acc);
+            const double h = block_sum(acc, scratch);
+            if (threadIdx.x == 0) hcol[c] = pass ? hcol[c] + h : h;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) v[i] = fma(-h, col[i], v[i]);
+        }
+    }
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc = fma(v[i], v[i], acc);
+    const double beta = sqrt(block_sum(acc, scratch));
+    const double inv = 1.0 / beta;  // no zero-norm guard in the reference (:35-36)
+    double* vnew = Vs + (long long)k * p.ldv;
+    const double* b = p.b + (long long)s * p.ldv;
+    acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double x = v[i] * inv;
+        vnew[i] = x;
+        v[i] = x;
+        acc = fma(x, b[i], acc);
+    }
+    const double btn = block_sum(acc, scratch);
+    if (threadIdx.x == 0) {
+        hcol[k] = beta;
+        p.bt[(long long)s * p.ncol + k] = btn;
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// Fold the new Gram row into S = ||V'V - I||_F^2 and, for TensorLanczosReorth, run the MGS fallback when
+// sqrt(S) > sqrt(eps) (orthogonal_bases.jl:119-131).  newcol = 0-based index of the newest column (= k for step k).
+// Executed by one whole CTA: the gram_row CTA of the mode that finishes last (ticket counter).
+// ------------------------------------------------------------------------------------------
+__device__ __noinline__ void monitor_body(const KrylovParams& p, int s, int newcol, int reorth, double* hcol, double* v,
+                                          double* scratch) {
+    const int n = p.n, k = newcol;  // k = reference step index
+    double* g = p.g + (long long)s * p.ncol;
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < newcol; j += blockDim.x) { const double gj = __ldcg(g + j); acc = fma(gj, gj, acc); }
+    double off2 = block_sum(acc, scratch);
+    double dd = __ldcg(g + newcol) - 1.0;
+    double Snew = p.S[s] + 2.0 * off2 + dd * dd;
+    if (reorth && sqrt(Snew) > SQRT_EPS) {
+        mgs_step_cta(p, s, k, v, hcol, scratch);
+        double* T = p.T + (long long)s * 3 * p.ncol;
+        if (threadIdx.x == 0) {
+            T[k - 1] = hcol[k - 1];                             // H[k,k]
+            if (k >= 2) T[2 * p.ncol + (k - 2)] = hcol[k - 2];  // H[k-1,k] keeps the MGS value; H[1:k-2,k] .= 0 (:129)
+            T[p.ncol + (k - 1)] = hcol[k];                      // beta = H[k+1,k] (:127)
+            T[2 * p.ncol + (k - 1)] = hcol[k];                  // update_subdiagonals! (:137)
+            p.fallbacks[s] += 1;
+        }
+        // Gram row of the replaced column (v holds the new v_{k+1})
+        const double* Vs = p.V + (long long)s * p.vstride;
+        off2 = 0.0;
+        for (int j = 0; j <= newcol; ++j) {
+            const double* col = Vs + (long long)j * p.ldv;
+            acc = 0.0;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) acc = fma(v[i], col[i], acc);
+            const double gj = block_sum(acc, scratch);
+            if (threadIdx.x == 0) g[j] = gj;
+            if (j < newcol) off2 = fma(gj, gj, off2);
+            else dd = gj - 1.0;
+        }
+        Snew = p.S[s] + 2.0 * off2 + dd * dd;
+    }
+    if (threadIdx.x == 0) {
+        p.S[s] = Snew;
+        if (s == p.mode0_local) p.orthS[newcol] = Snew;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Orthogonality monitor: the newest row of the Gram matrix V'V.
 //   g[s][j] = V_s[:,j] . V_s[:,ncols-1],  j = 0..ncols-1
 // The reference forms the whole (k+1)x(k+1) Gram matrix with dgemm at every step in every mode
@@ -120,8 +207,9 @@ __global__ void __launch_bounds__(512) lanczos_ttr_kernel(KrylovParams p, int k)
 constexpr int GRAM_PSTRIDE = 16;   // partial sums per column (>= warps per column)
 
 template <int U, int THREADS>   // U = 16-byte loads in flight per lane and column (two columns are streamed at once)
-__global__ void __launch_bounds__(THREADS) gram_row_kernel(KrylovParams p, int ncols, int cols_per_cta, int mode_base,
-                                                       int w_in_smem, int wpc) {
+__global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 2 : 1)) gram_row_kernel(KrylovParams p, int ncols, int cols_per_cta, int mode_base,
+                                                       int w_in_smem, int wpc, int monitor /* -1 none, 0, 1 = reorth */,
+                                                       unsigned int* tickets, double* vscratch) {
     // wpc = warps that share one column: every column is cut into wpc contiguous segments so all warps of the
     // CTA stream equal amounts, whatever the number of columns.
     if (*p.status != ST_RUNNING) return;
@@ -131,8 +219,11 @@ __global__ void __launch_bounds__(THREADS) gram_row_kernel(KrylovParams p, int n
     const double* Vs = p.V + (long long)s * p.vstride;
     const double* wg = Vs + (long long)(ncols - 1) * p.ldv;
     const int nq = n >> 1;
+    __shared__ double scratch[32];
+    __shared__ unsigned int my_ticket;
     double* part = smem;                                  // [cols_per_cta][GRAM_PSTRIDE] partial sums
-    double* wsm = smem + (size_t)cols_per_cta * GRAM_PSTRIDE;
+    double* hcol = smem + (size_t)cols_per_cta * GRAM_PSTRIDE;              // ncol doubles (MGS fallback)
+    double* wsm = hcol + ((p.ncol + 1) & ~1);
     if (w_in_smem) {
         const double2* w2g = reinterpret_cast<const double2*>(wg);
         double2* s2 = reinterpret_cast<double2*>(wsm);
@@ -200,49 +291,17 @@ __global__ void __launch_bounds__(THREADS) gram_row_kernel(KrylovParams p, int n
         for (int sgi = 0; sgi < wpc; ++sgi) acc += part[(j - c0) * GRAM_PSTRIDE + sgi];
         g[j] = acc;
     }
-}
-
-// ------------------------------------------------------------------------------------------
-// CTA-wide modified Gram-Schmidt step k (orthogonal_bases.jl:15-37) for mode s.
-// v: working vector of n doubles (shared or global scratch); every thread owns the rows
-// i = tid, tid + blockDim, ... so the dot/axpy sequence needs no barrier besides the reduction.
-// hcol[0..k-1] = H[1:k,k], hcol[k] = H[k+1,k].  Writes V[:,k+1] and b~[k+1].
-// ------------------------------------------------------------------------------------------
-__device__ void mgs_step_cta(const KrylovParams& p, int s, int k, double* v, double* hcol, double* scratch) {
-    const int n = p.n;
-    const OpDesc& op = p.ops[p.mode_op[s]];
-    double* Vs = p.V + (long long)s * p.vstride;
-    const double* vk = Vs + (long long)(k - 1) * p.ldv;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) v[i] = apply_row(op, vk, i, n);
-    for (int pass = 0; pass < 2; ++pass) {
-        for (int c = 0; c < k; ++c) {
-            const double* col = Vs + (long long)c * p.ldv;
-            double acc = 0.0;
-            for (int i = threadIdx.x; i < n; i += blockDim.x) acc = fma(v[i], col[i], acc);
-            const double h = block_sum(acc, scratch);
-            if (threadIdx.x == 0) hcol[c] = pass ? hcol[c] + h : h;
-            for (int i = threadIdx.x; i < n; i += blockDim.x) v[i] = fma(-h, col[i], v[i]);
-        }
-    }
-    double acc = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) acc = fma(v[i], v[i], acc);
-    const double beta = sqrt(block_sum(acc, scratch));
-    const double inv = 1.0 / beta;  // no zero-norm guard in the reference (:35-36)
-    double* vnew = Vs + (long long)k * p.ldv;
-    const double* b = p.b + (long long)s * p.ldv;
-    acc = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const double x = v[i] * inv;
-        vnew[i] = x;
-        v[i] = x;
-        acc = fma(x, b[i], acc);
-    }
-    const double btn = block_sum(acc, scratch);
-    if (threadIdx.x == 0) {
-        hcol[k] = beta;
-        p.bt[(long long)s * p.ncol + k] = btn;
-    }
+    if (monitor < 0) return;
+    // the CTA of this mode that finishes last folds the row into S (and runs the MGS fallback if needed)
+    __threadfence();
     __syncthreads();
+    if (threadIdx.x == 0) my_ticket = atomicAdd(tickets + s, 1u);
+    __syncthreads();
+    if (my_ticket != gridDim.x - 1) return;
+    __threadfence();
+    double* v = w_in_smem ? wsm : vscratch + (long long)s * p.ldv;
+    monitor_body(p, s, ncols - 1, monitor, hcol, v, scratch);
+    if (threadIdx.x == 0) tickets[s] = 0u;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -338,56 +397,6 @@ __global__ void __launch_bounds__(THREADS) arnoldi_mgs_reg_kernel(KrylovParams p
         double* T = p.T + (long long)s * 3 * p.ncol;
         T[k - 1] = hcol[k - 1];
         T[p.ncol + (k - 1)] = beta;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// After gram_row_kernel: fold the new Gram row into S = ||V'V - I||_F^2 and, for
-// TensorLanczosReorth, run the MGS fallback when sqrt(S) > sqrt(eps) (orthogonal_bases.jl:119-131).
-// newcol = 0-based index of the newest column (= k for step k).  One CTA per listed mode;
-// CTAs whose mode does not fall back leave after a k-term sum.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) monitor_kernel(KrylovParams p, int newcol, int mode_base, int reorth,
-                                                      double* vscratch /* [modes][ldv] or nullptr -> shared */) {
-    if (*p.status != ST_RUNNING) return;
-    extern __shared__ double smem[];
-    __shared__ double scratch[32];
-    const int s = mode_base + blockIdx.x, n = p.n, k = newcol;  // k = reference step index
-    double* g = p.g + (long long)s * p.ncol;
-    double acc = 0.0;
-    for (int j = threadIdx.x; j < newcol; j += blockDim.x) acc = fma(g[j], g[j], acc);
-    double off2 = block_sum(acc, scratch);
-    double dd = g[newcol] - 1.0;
-    double Snew = p.S[s] + 2.0 * off2 + dd * dd;
-    if (reorth && sqrt(Snew) > SQRT_EPS) {
-        double* hcol = smem;                                   // ncol doubles
-        double* v = vscratch ? vscratch + (long long)s * p.ldv : smem + p.ncol;
-        mgs_step_cta(p, s, k, v, hcol, scratch);
-        double* T = p.T + (long long)s * 3 * p.ncol;
-        if (threadIdx.x == 0) {
-            T[k - 1] = hcol[k - 1];                             // H[k,k]
-            if (k >= 2) T[2 * p.ncol + (k - 2)] = hcol[k - 2];  // H[k-1,k] keeps the MGS value; H[1:k-2,k] .= 0 (:129)
-            T[p.ncol + (k - 1)] = hcol[k];                      // beta = H[k+1,k] (:127)
-            T[2 * p.ncol + (k - 1)] = hcol[k];                  // update_subdiagonals! (:137)
-            p.fallbacks[s] += 1;
-        }
-        // Gram row of the replaced column (v holds the new v_{k+1})
-        const double* Vs = p.V + (long long)s * p.vstride;
-        off2 = 0.0;
-        for (int j = 0; j <= newcol; ++j) {
-            const double* col = Vs + (long long)j * p.ldv;
-            acc = 0.0;
-            for (int i = threadIdx.x; i < n; i += blockDim.x) acc = fma(v[i], col[i], acc);
-            const double gj = block_sum(acc, scratch);
-            if (threadIdx.x == 0) g[j] = gj;
-            if (j < newcol) off2 = fma(gj, gj, off2);
-            else dd = gj - 1.0;
-        }
-        Snew = p.S[s] + 2.0 * off2 + dd * dd;
-    }
-    if (threadIdx.x == 0) {
-        p.S[s] = Snew;
-        if (s == p.mode0_local) p.orthS[newcol] = Snew;
     }
 }
 
