@@ -71,6 +71,18 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
     return warp_sum(r);
 }
 
+// Two sums at once (same barriers).  scratch: >= 64 doubles.
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* scratch) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    __syncthreads();
+    if (lane == 0) { scratch[w] = a; scratch[32 + w] = b; }
+    __syncthreads();
+    a = warp_sum((lane < nw) ? scratch[lane] : 0.0);
+    b = warp_sum((lane < nw) ? scratch[32 + lane] : 0.0);
+}
+
 // Row i of A_s times v.  Accumulates in ascending column order, like the reference's CSC
 // product (SparseArrays mul!, called at orthogonal_bases.jl:20,45,103).
 __device__ __forceinline__ double apply_row(const OpDesc& op, const double* __restrict__ v, int i, int n) {

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(512) init_basis_kernel(KrylovParams p, double*
 // 3-term Lanczos step k for every mode.  CPM CTAs (one thread-block cluster) share a mode and
 // split the rows; the three reductions go through distributed shared memory.
 //   u = A v_k - beta_{k-1} v_{k-1};  H[k,k] = u.v_k;  v^ = u - H[k,k] v_k;  beta = ||v^||
-//   v_{k+1} = v^ / beta (zeros if beta == 0);  H[k+1,k] = H[k,k+1] = beta;  b~[k+1] = v_{k+1}.b
+//   v_{k+1} = v^ / beta (zeros if beta == 0);  H[k+1,k] = H[k,k+1] = beta;  b~[k+1] = v_{k+1}.b = (v^.b)/beta
 // Algorithmic HBM bytes per mode: (ndiag + 4) * 8 * n  (diagonals, v_k, v_{k-1}, b read; v_{k+1} written).
 // ------------------------------------------------------------------------------------------
 template <int CPM>
@@ -60,7 +60,7 @@ template <int CPM>
 __global__ void __launch_bounds__(512) lanczos_ttr_kernel(KrylovParams p, int k) {
     if (*p.status != ST_RUNNING) return;
     extern __shared__ double smem[];
-    __shared__ double scratch[32];
+    __shared__ double scratch[64];
     __shared__ double slots[4];
     const int s = blockIdx.x / CPM, part = blockIdx.x % CPM, n = p.n;
     const int chunk = (((n + CPM - 1) / CPM) + 1) & ~1;
@@ -83,23 +83,34 @@ __global__ void __launch_bounds__(512) lanczos_ttr_kernel(KrylovParams p, int k)
     }
     const double alpha = cluster_sum<CPM>(block_sum(acc, scratch), &slots[0]);
 
+    // second and last reduction round: ||v^||^2 and v^.b together (b~[k+1] = v_{k+1}.b = (v^.b)/beta)
+    const double* b = p.b + (long long)s * p.ldv;
+    double accb = 0.0;
     acc = 0.0;
     for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
         const double w = u[i - lo] - alpha * vk[i];
         u[i - lo] = w;
         acc = fma(w, w, acc);
+        accb = fma(w, b[i], accb);
     }
-    const double beta = sqrt(cluster_sum<CPM>(block_sum(acc, scratch), &slots[1]));
-
+    block_sum2(acc, accb, scratch);
+    double beta2 = acc, vb = accb;
+    if (CPM > 1) {
+        cg::cluster_group cl = cg::this_cluster();
+        if (threadIdx.x == 0) { slots[1] = acc; slots[2] = accb; }
+        cl.sync();
+        beta2 = 0.0; vb = 0.0;
+#pragma unroll
+        for (int r = 0; r < CPM; ++r) {
+            const double* rs = cl.map_shared_rank(slots, r);
+            beta2 += rs[1];
+            vb += rs[2];
+        }
+    }
+    const double beta = sqrt(beta2);
     const double inv = (beta == 0.0) ? 0.0 : 1.0 / beta;
-    const double* b = p.b + (long long)s * p.ldv;
-    acc = 0.0;
-    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        const double x = inv * u[i - lo];
-        vnew[i] = x;
-        acc = fma(x, b[i], acc);
-    }
-    const double btn = cluster_sum<CPM>(block_sum(acc, scratch), &slots[2]);
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) vnew[i] = inv * u[i - lo];
+    const double btn = inv * vb;
     if (part == 0 && threadIdx.x == 0) {
         T[k - 1] = alpha;                   // H[k,k]
         T[p.ncol + (k - 1)] = beta;         // H[k+1,k]
