@@ -98,6 +98,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic_ratio():
+    """DRAM bytes / algorithmic bytes of the Gram-row kernel from the committed `ncu --set full` capture."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_gram_traffic.json")))
+        return float(t["traffic_over_algorithmic"]), "profiles/r01_gram_traffic.json (ncu dram__bytes_read+write, launches with 31-33 columns)"
+    except Exception:
+        return None, None
+
+
 def measured_peak():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
@@ -308,6 +317,7 @@ def run_b200(a):
     value = iters / (dev_ms / 1e3)
     peak, peak_kind = measured_peak()
     achieved = gram_bytes / (gram_ms / 1e3) / 1e9 if gram_ms > 0 else 0.0
+    tr_ratio, tr_src = measured_traffic_ratio()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -329,7 +339,8 @@ def run_b200(a):
                      "frac_of_nominal_8TBs": achieved / 8000.0, "launches": gram_n,
                      "algorithmic_bytes_per_launch_avg": gram_bytes / max(gram_n, 1),
                      "avg_launch_ms": gram_ms / max(gram_n, 1), "share_of_step": gram_ms / dev_ms,
-                     "traffic": None,
+                     "traffic": (tr_ratio * gram_bytes / max(gram_n, 1)) if (tr_ratio and world == 1) else None,
+                     "traffic_source": tr_src,
                      "ttr_kernel": {"achieved": (ttr_bytes / (ttr_ms / 1e3) / 1e9) if ttr_ms > 0 else None,
                                     "share_of_step": ttr_ms / dev_ms}},
     }
