@@ -158,7 +158,10 @@ int tk_tridiag_eig_batched(int32_t device, int32_t nb, int32_t k, const double* 
 
 /* which: 0 = 3-term Lanczos step, 1 = orthogonality-monitor Gram row, 2 = Arnoldi/MGS step,
  * 3 = eigensolver, 4 = CP assembly + Gram, 5 = cross-mode combine, 6 = the whole last tk_solve
- * (CUDA events on the handle's stream, first enqueue to last kernel).  Sums over the last tk_solve. */
+ * (CUDA events on the handle's stream, first enqueue to last kernel), 7 = from the last tk_timing_mark to the end of
+ * the last tk_solve (one device-side window around several solves).  Sums over the last tk_solve. */
+/* records the start of a timed region on the handle's stream (read it back with which = 7) */
+int tk_timing_mark(tk_handle* h);
 int tk_get_timing(tk_handle* h, int32_t which, double* ms_total, int64_t* launches, double* algorithmic_bytes);
 int tk_launch_count(tk_handle* h, int64_t* launches);
 

@@ -31,7 +31,7 @@ EXPORTS = [
     "tk_set_schedule", "tk_schedule_laplace", "tk_solve", "tk_solution_rank", "tk_get_solution", "tk_get_solution_all",
     "tk_begin", "tk_step_bases", "tk_compress", "tk_residual",
     "tk_get_H", "tk_get_V", "tk_get_bt", "tk_get_Y", "tk_get_eig", "tk_get_orth_state",
-    "tk_tridiag_eig_batched", "tk_get_timing", "tk_launch_count",
+    "tk_tridiag_eig_batched", "tk_timing_mark", "tk_get_timing", "tk_launch_count",
 ]
 
 
@@ -86,6 +86,7 @@ def _load():
         "tk_get_eig": (C.c_int, [p, i32, i32, pd, pd]),
         "tk_get_orth_state": (C.c_int, [p, i32, pd, pi32]),
         "tk_tridiag_eig_batched": (C.c_int, [i32, i32, i32, pd, pd, pd, pd, pi32]),
+        "tk_timing_mark": (C.c_int, [p]),
         "tk_get_timing": (C.c_int, [p, i32, pd, pi64, pd]),
         "tk_launch_count": (C.c_int, [p, pi64]),
     }

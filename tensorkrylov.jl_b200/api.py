@@ -337,6 +337,9 @@ class Solver:
         check(lib.tk_get_orth_state(self.h, s, C.byref(S), C.byref(fb)))
         return S.value, fb.value
 
+    def timing_mark(self):
+        check(lib.tk_timing_mark(self.h))
+
     def timing(self, which):
         ms, n, by = C.c_double(), C.c_int64(), C.c_double()
         check(lib.tk_get_timing(self.h, which, C.byref(ms), C.byref(n), C.byref(by)))

@@ -197,7 +197,7 @@ struct SchedEntry {
     size_t off = 0;  // into the alpha/omega pools
 };
 
-enum { TM_TTR = 0, TM_GRAM = 1, TM_MGS = 2, TM_EIG = 3, TM_ASM = 4, TM_COMBINE = 5, TM_SOLVE = 6, TM_KINDS = 7 };
+enum { TM_TTR = 0, TM_GRAM = 1, TM_MGS = 2, TM_EIG = 3, TM_ASM = 4, TM_COMBINE = 5, TM_SOLVE = 6, TM_REGION = 7, TM_KINDS = 8 };
 
 }  // namespace tk
 
@@ -266,6 +266,7 @@ struct tk_handle {
     std::vector<Timed> timed;
     std::vector<cudaEvent_t> ev_pool;
     cudaEvent_t ev_solve[2] = {nullptr, nullptr};
+    cudaEvent_t ev_region = nullptr;   // tk_timing_mark: start of a multi-solve timed region
     size_t ev_used = 0;
     double tm_ms[TM_KINDS] = {0}, tm_bytes[TM_KINDS] = {0};
     long long tm_launches[TM_KINDS] = {0};
@@ -1032,6 +1033,7 @@ void tk_destroy(tk_handle* h) {
     for (auto st : h->stream3) if (st) cudaStreamSynchronize(st);
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     for (auto e : h->ev_solve) if (e) cudaEventDestroy(e);
+    if (h->ev_region) cudaEventDestroy(h->ev_region);
     for (auto e : h->ring_ev) cudaEventDestroy(e);
     if (h->status_ring) cudaFreeHost(h->status_ring);
     for (auto e : h->step_ev) cudaEventDestroy(e);
@@ -1571,8 +1573,25 @@ int tk_tridiag_eig_batched(int32_t device, int32_t nb, int32_t k, const double* 
     return 0;
 }
 
+int tk_timing_mark(tk_handle* h) {
+    if (!h) return set_error(TK_EINVAL, "null handle");
+    TK_CUDA(cudaSetDevice(h->device));
+    if (!h->ev_region) TK_CUDA(cudaEventCreate(&h->ev_region));
+    TK_CUDA(cudaEventRecord(h->ev_region, h->stream));
+    return 0;
+}
+
 int tk_get_timing(tk_handle* h, int32_t which, double* ms_total, int64_t* launches, double* algorithmic_bytes) {
     if (!h || which < 0 || which >= TM_KINDS) return set_error(TK_EINVAL, "bad timing kind %d", which);
+    if (which == TM_REGION) {
+        if (!h->ev_region || !h->ev_solve[1]) return set_error(TK_ESTATE, "no timed region (tk_timing_mark, then tk_solve)");
+        float ms = 0.f;
+        TK_CUDA(cudaEventElapsedTime(&ms, h->ev_region, h->ev_solve[1]));
+        if (ms_total) *ms_total = ms;
+        if (launches) *launches = 0;
+        if (algorithmic_bytes) *algorithmic_bytes = 0.0;
+        return 0;
+    }
     if (ms_total) *ms_total = h->tm_ms[which];
     if (launches) *launches = h->tm_launches[which];
     if (algorithmic_bytes) *algorithmic_bytes = h->tm_bytes[which];
