@@ -211,6 +211,7 @@ struct tk_handle {
     int instance = 0, matrixclass = 0, variant = 0, flags = 0, device = 0, rank = 0, world = 1;
     long long ldv = 0;
     int per_mode = 0, ncls = 1;
+    bool use_expm = false;   // compressed solve through the dense exponential (NonSymInstance, and the EigValMat class)
     int chunk_modes = 16, nchunks = 1, chunk_base = 0;
     cudaStream_t stream = nullptr;    // Krylov-step kernels (1)
     cudaStream_t stream2 = nullptr;   // CP assembly + residual (3)(4): runs behind the Krylov steps, concurrently
@@ -385,7 +386,7 @@ static int alloc_work(tk_handle* h) {
     TK_TRY(h->ticket_d.alloc(1));
     TK_TRY(h->merged.alloc((size_t)h->pstride_max));
     if (h->world > 1) TK_TRY(h->gathered.alloc((size_t)h->world * h->pstride_max));
-    if (h->instance == TK_NONSYM) {
+    if (h->use_expm) {
         h->ex_ld = (h->nmax + 3) & ~3;
         // exponentials of up to ring_depth iterations are in flight (they only depend on the Krylov step); with one
         // matrix class the ring is cheap, with per-mode classes it is kept at depth 1
@@ -668,7 +669,7 @@ static int enqueue_expm(tk_handle* h, int k, cudaStream_t st);
 // solve_compressed_system (tensor_krylov_method.jl:10-34), first half: the eigendecomposition(s), or for
 // NonSymInstance the dense exponentials exp(gamma_j H)
 static int enqueue_eig(tk_handle* h, int k) {
-    if (h->instance == TK_NONSYM) return enqueue_expm(h, k, h->stream3[k % tk_handle::NEIG]);
+    if (h->use_expm) return enqueue_expm(h, k, h->stream3[k % tk_handle::NEIG]);
     // under TK_FLAG_REFERENCE_H1 the one problem is mode 1's H (this rank's own copy or its shadow copy)
     const double* Tsrc = h->per_mode ? h->T.p : h->T.p + (size_t)h->eig_slot * 3 * h->ncol;
     CompressParams c = make_cp(h, k);
@@ -774,7 +775,7 @@ static int enqueue_expm(tk_handle* h, int k, cudaStream_t st) {
 
 // second half: CP assembly of Y_s for every local mode
 static int enqueue_assemble(tk_handle* h, int k) {
-    if (h->instance == TK_NONSYM) return enqueue_expm_apply(h, k);
+    if (h->use_expm) return enqueue_expm_apply(h, k);
     CompressParams c = make_cp(h, k);
     const size_t smem = ((size_t)2 * k + (size_t)k * ASM_TJ) * 8;
     TK_TRY(allow_smem(assemble_cp_kernel, smem));
@@ -791,7 +792,7 @@ static int enqueue_assemble(tk_handle* h, int k) {
 // residualnorm! (utils.jl:402-443) + exits of the loop body (tensor_krylov_method.jl:85-118)
 static int enqueue_residual(tk_handle* h, int k, double tol) {
     CompressParams c = make_cp(h, k);
-    if (h->dl > 0 && h->instance == TK_NONSYM) {      // the symmetric path did this inside assemble_cp_kernel
+    if (h->dl > 0 && h->use_expm) {      // the symmetric path did this inside assemble_cp_kernel
         TimedScope ts(h, TM_ASM, 0.0, h->stream2);
         gram_blocks_kernel<<<h->dl, 256, 0, h->stream2>>>(c);
         h->launches++;
@@ -958,6 +959,10 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
     h->chunk_base = h->first % mc;
     h->nchunks = std::max(1, (per + mc - 1) / mc + ((per % mc) && world > 1 ? 1 : 0));
     h->per_mode = (flags & TK_FLAG_REFERENCE_H1) ? 0 : 1;
+    // EigValMat has its own method in the reference (utils.jl:525-546): every mode exponentiates its OWN H_s, and on
+    // the raw view -- which stops being symmetric after the first MGS fallback -- so it takes the dense exponential
+    if (matrixclass == TK_EIGVALMAT) h->per_mode = 1;
+    h->use_expm = (instance == TK_NONSYM) || (matrixclass == TK_EIGVALMAT);
     h->ncls = h->per_mode ? std::max(h->dl, 1) : 1;
     const bool shadow = !h->per_mode && h->first != 0;   // every rank advances its own copy of mode 1: no broadcast needed
     h->dk = h->dl + (shadow ? 1 : 0);

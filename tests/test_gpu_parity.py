@@ -451,6 +451,28 @@ def test_solve_matches_reference_history_laplace_d5(tk, gpu):
     assert np.all(cd.orthogonality_data[1:] < 1e-8)
 
 
+def test_solve_matches_reference_history_eigvalmat_d5(tk, gpu):
+    """The reference's stored run eigenvalues_data/dzero (Julia): EigValMat with the clustered spectrum j^2/n^2,
+    TensorLanczosReorth.  Orthogonality is lost around k = 60, the MGS fallback fires from then on and leaves H
+    un-symmetric; the reference's EigValMat method exponentiates each mode's raw H_s (utils.jl:525-546)."""
+    g = golden("eigval_dzero")
+    d, n, nmax = 5, 200, 110
+    ev = np.array([(j * j) * (1.0 / (n * n)) for j in range(1, n + 1)])
+    A = tk.KroneckerMatrix(tk.SymInstance, [tk.assemble_matrix(ev, tk.EigValMat)] * d, tk.EigValMat)
+    system = tk.TensorizedSystem(tk.SymInstance, A, [g["rhs_d5"]] * d)
+    out = []
+    cd = tk.ConvergenceData(nmax)
+    tk.tensorkrylov(cd, system.A, system.b, 1e-9, nmax, tk.TensorLanczosReorth, verbose=False, solver_out=out)
+    rr = g["relres_d5"]
+    assert out[0].orth_state(0)[1] > 0, "the fallback must have fired"
+    out[0].close()
+    k = np.arange(2, 56)
+    assert np.max(np.abs(cd.relative_residual_norm[k - 1] - rr[k - 1]) / rr[k - 1]) < 1e-9
+    k = np.arange(56, nmax + 1)
+    assert np.max(np.abs(cd.relative_residual_norm[k - 1] - rr[k - 1]) / rr[k - 1]) < 1e-6
+    assert np.all(cd.orthogonality_data[1:] < 3e-8)      # the stored loss clamps at sqrt(eps) = 1.49e-8
+
+
 @pytest.mark.parametrize("d", [10, 50])
 def test_solve_matches_reference_history_laplace_more_modes(tk, gpu, d):
     g = golden("laplace_new")
