@@ -31,7 +31,9 @@ dist.broadcast(buf, 0)
 uid = bytes(buf.cpu().numpy().tobytes())
 d, n, nmax, tol = {d}, {n}, {nmax}, {tol}
 rng = np.random.default_rng(5)
-A1 = tk.assemble_matrix(n, tk.Laplace)
+NONSYM = {nonsym}
+inst, cls, variant = (tk.NonSymInstance, tk.ConvDiff, tk.TensorArnoldi) if NONSYM else (tk.SymInstance, tk.Laplace, tk.TensorLanczosReorth)
+A1 = tk.assemble_matrix(n, cls)
 if {distinct}:
     b = [v / np.linalg.norm(v) for v in (rng.random(n) for _ in range(d))]
 else:
@@ -42,7 +44,7 @@ out = {{}}
 for label, w, r, u in (("multi", world, rank, uid), ("single", 1, 0, None)):
     if label == "single" and rank != 0:
         continue
-    s = tk.Solver(d, n, nmax, tk.SymInstance, tk.Laplace, tk.TensorLanczosReorth, flags=flags, device=rank, rank=r, world=w,
+    s = tk.Solver(d, n, nmax, inst, cls, variant, flags=flags, device=rank, rank=r, world=w,
                   unique_id=u)
     s.set_operators([A1] * d); s.set_rhs(b); s.set_schedule(A1, tol)
     res = s.solve(tol)
@@ -68,15 +70,18 @@ def _ngpus(tk):
     return tk.device_count()
 
 
-@pytest.mark.parametrize("d,n,nmax,tol,distinct,ref_h1", [(48, 600, 14, 1e-8, False, True), (37, 400, 10, 1e-8, True, False),
-                                                        (64, 1000, 40, 1e-4, False, True)])
-def test_two_gpu_solve_equals_single_gpu(tk, gpu, tmp_path, d, n, nmax, tol, distinct, ref_h1):
+@pytest.mark.parametrize("d,n,nmax,tol,distinct,ref_h1,nonsym", [(48, 600, 14, 1e-8, False, True, False),
+                                                               (37, 400, 10, 1e-8, True, False, False),
+                                                               (64, 1000, 40, 1e-4, False, True, False),
+                                                               (20, 300, 12, 1e-8, False, True, True),
+                                                               (9, 200, 10, 1e-8, True, False, True)])
+def test_two_gpu_solve_equals_single_gpu(tk, gpu, tmp_path, d, n, nmax, tol, distinct, ref_h1, nonsym):
     if _ngpus(tk) < 2:
         pytest.skip("needs two GPUs")
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     flags = tk.TK_FLAG_REFERENCE_H1 if ref_h1 else 0
     script = tmp_path / "worker.py"
-    script.write_text(WORKER.format(root=ROOT, d=d, n=n, nmax=nmax, tol=tol, distinct=distinct, flags=flags))
+    script.write_text(WORKER.format(root=ROOT, d=d, n=n, nmax=nmax, tol=tol, distinct=distinct, flags=flags, nonsym=nonsym))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE="2")
     procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
