@@ -203,7 +203,55 @@ enum { TM_TTR = 0, TM_GRAM = 1, TM_MGS = 2, TM_EIG = 3, TM_ASM = 4, TM_COMBINE =
 
 using namespace tk;
 
+// Streams, events and the pinned status ring of a handle.  Creating and destroying them (cudaMallocHost/cudaFreeHost
+// in particular) costs far more than a solve, so destroyed handles park the bundle in a process-level free list.
+struct tk_resources {
+    int device = 0;
+    cudaStream_t s_main = nullptr, s_asm = nullptr, s_eig[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t step_ev[8], eig_ev[8], asm_ev[8], ring_ev[8], ev_solve[2], ev_region;
+    int* status_ring = nullptr;
+    std::vector<cudaEvent_t> ev_pool;   // timing events, grown on demand
+};
+static std::vector<tk_resources*> g_res_free;
+
+static int acquire_resources(int device, tk_resources** out) {
+    {
+        std::lock_guard<std::mutex> lock(g_mutex);
+        for (size_t i = 0; i < g_res_free.size(); ++i)
+            if (g_res_free[i]->device == device) {
+                *out = g_res_free[i];
+                g_res_free.erase(g_res_free.begin() + i);
+                return 0;
+            }
+    }
+    std::unique_ptr<tk_resources> r(new tk_resources());
+    r->device = device;
+    TK_CUDA(cudaStreamCreateWithFlags(&r->s_main, cudaStreamNonBlocking));
+    TK_CUDA(cudaStreamCreateWithFlags(&r->s_asm, cudaStreamNonBlocking));
+    for (auto& st : r->s_eig) TK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) {
+        TK_CUDA(cudaEventCreateWithFlags(&r->step_ev[i], cudaEventDisableTiming));
+        TK_CUDA(cudaEventCreateWithFlags(&r->eig_ev[i], cudaEventDisableTiming));
+        TK_CUDA(cudaEventCreateWithFlags(&r->asm_ev[i], cudaEventDisableTiming));
+        TK_CUDA(cudaEventCreateWithFlags(&r->ring_ev[i], cudaEventDisableTiming));
+    }
+    TK_CUDA(cudaEventCreate(&r->ev_solve[0]));
+    TK_CUDA(cudaEventCreate(&r->ev_solve[1]));
+    TK_CUDA(cudaEventCreate(&r->ev_region));
+    TK_CUDA(cudaMallocHost(&r->status_ring, 8 * sizeof(int)));
+    *out = r.release();
+    return 0;
+}
+
 struct tk_handle {
+    tk_resources* res = nullptr;
+    ~tk_handle() {
+        if (res) {                      // also on a failed tk_create
+            res->ev_pool.swap(ev_pool);
+            std::lock_guard<std::mutex> lock(g_mutex);
+            g_res_free.push_back(res);
+        }
+    }
     int d = 0, dl = 0, first = 0, nmax = 0, ncol = 0, n = 0;
     int dk = 0;          // modes the Krylov kernels advance: dl, plus a shadow copy of global mode 0 (slot dl) when the
                          // reference's H_1-for-all-modes rule is on and another rank owns mode 0
@@ -968,19 +1016,23 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
     h->dk = h->dl + (shadow ? 1 : 0);
     h->eig_slot = shadow ? h->dl : 0;
 
-    TK_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    if (env_int("TK_SINGLE_STREAM", 0)) h->stream2 = h->stream;
-    else TK_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    TK_TRY(acquire_resources(device, &h->res));
+    tk_resources* r = h->res;
+    h->stream = r->s_main;
+    h->stream2 = env_int("TK_SINGLE_STREAM", 0) ? h->stream : r->s_asm;
     for (int i = 0; i < tk_handle::NEIG; ++i) {
         if (env_int("TK_SINGLE_STREAM", 0) || env_int("TK_TWO_STREAMS", 0)) h->stream3[i] = h->stream2;
-        else if (i >= env_int("TK_EIG_STREAMS", tk_handle::NEIG)) h->stream3[i] = h->stream3[0];
-        else TK_CUDA(cudaStreamCreateWithFlags(&h->stream3[i], cudaStreamNonBlocking));
+        else if (i >= env_int("TK_EIG_STREAMS", tk_handle::NEIG)) h->stream3[i] = r->s_eig[0];
+        else h->stream3[i] = r->s_eig[i];
     }
-    h->eig_ev.resize(8); h->asm_ev.resize(8);
-    for (auto& e : h->eig_ev) TK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (auto& e : h->asm_ev) TK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    h->step_ev.resize(8);
-    for (auto& e : h->step_ev) TK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->eig_ev.assign(r->eig_ev, r->eig_ev + 8);
+    h->asm_ev.assign(r->asm_ev, r->asm_ev + 8);
+    h->step_ev.assign(r->step_ev, r->step_ev + 8);
+    h->ring_ev.assign(r->ring_ev, r->ring_ev + 8);
+    h->ev_solve[0] = r->ev_solve[0]; h->ev_solve[1] = r->ev_solve[1];
+    h->ev_region = r->ev_region;
+    h->status_ring = r->status_ring;
+    h->ev_pool.swap(r->ev_pool);
     const size_t dl = std::max(h->dk, 1);
     TK_TRY(h->V.alloc(dl * (size_t)h->ncol * h->ldv, false));
     TK_TRY(h->b.alloc(dl * (size_t)h->ldv));
@@ -1006,9 +1058,6 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
     h->mode_op.assign(dl, -1);
     h->rhs_set.assign(dl, 0);
     h->sched.assign(nmax + 1, SchedEntry());
-    TK_CUDA(cudaMallocHost(&h->status_ring, 8 * sizeof(int)));
-    h->ring_ev.resize(8);
-    for (auto& e : h->ring_ev) TK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     if (world > 1) {
         TK_TRY(nccl_bind());
         const std::string key(static_cast<const char*>(unique_id), 128);
@@ -1036,27 +1085,24 @@ void tk_destroy(tk_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->stream2) cudaStreamSynchronize(h->stream2);
     for (auto st : h->stream3) if (st) cudaStreamSynchronize(st);
-    for (auto e : h->ev_pool) cudaEventDestroy(e);
-    for (auto e : h->ev_solve) if (e) cudaEventDestroy(e);
-    if (h->ev_region) cudaEventDestroy(h->ev_region);
-    for (auto e : h->ring_ev) cudaEventDestroy(e);
-    if (h->status_ring) cudaFreeHost(h->status_ring);
-    for (auto e : h->step_ev) cudaEventDestroy(e);
-    for (auto e : h->eig_ev) cudaEventDestroy(e);
-    for (auto e : h->asm_ev) cudaEventDestroy(e);
-    for (int i = 0; i < tk_handle::NEIG; ++i) {
-        cudaStream_t st = h->stream3[i];
-        bool dup = (st == h->stream2 || st == h->stream || st == nullptr);
-        for (int j = 0; j < i; ++j) dup = dup || (h->stream3[j] == st);
-        if (!dup) cudaStreamDestroy(st);
-    }
-    if (h->stream) cudaStreamDestroy(h->stream);
-    if (h->stream2 && h->stream2 != h->stream) cudaStreamDestroy(h->stream2);
-    delete h;
+    delete h;                           // parks streams, events and the pinned ring for the next handle
 }
 
 int tk_release_cache(void) {
     std::lock_guard<std::mutex> lock(g_mutex);
+    for (tk_resources* r : g_res_free) {
+        cudaSetDevice(r->device);
+        cudaStreamDestroy(r->s_main); cudaStreamDestroy(r->s_asm);
+        for (auto st : r->s_eig) cudaStreamDestroy(st);
+        for (int i = 0; i < 8; ++i) {
+            cudaEventDestroy(r->step_ev[i]); cudaEventDestroy(r->eig_ev[i]); cudaEventDestroy(r->asm_ev[i]); cudaEventDestroy(r->ring_ev[i]);
+        }
+        cudaEventDestroy(r->ev_solve[0]); cudaEventDestroy(r->ev_solve[1]); cudaEventDestroy(r->ev_region);
+        for (auto e : r->ev_pool) cudaEventDestroy(e);
+        cudaFreeHost(r->status_ring);
+        delete r;
+    }
+    g_res_free.clear();
     pool_trim();
     return 0;
 }
@@ -1322,7 +1368,6 @@ int tk_solve(tk_handle* h, double tol, int32_t* status, int64_t* niter, int32_t*
     TK_CUDA(cudaSetDevice(h->device));
     TK_TRY(upload_schedule(h));
     TK_TRY(alloc_work(h));
-    if (!h->ev_solve[0]) { TK_CUDA(cudaEventCreate(&h->ev_solve[0])); TK_CUDA(cudaEventCreate(&h->ev_solve[1])); }
     TK_CUDA(cudaEventRecord(h->ev_solve[0], h->stream));
     TK_TRY(begin_solve(h));
     // Two streams: `stream` advances the Krylov bases (iteration k+1 needs nothing from the compressed solve of
@@ -1581,7 +1626,6 @@ int tk_tridiag_eig_batched(int32_t device, int32_t nb, int32_t k, const double* 
 int tk_timing_mark(tk_handle* h) {
     if (!h) return set_error(TK_EINVAL, "null handle");
     TK_CUDA(cudaSetDevice(h->device));
-    if (!h->ev_region) TK_CUDA(cudaEventCreate(&h->ev_region));
     TK_CUDA(cudaEventRecord(h->ev_region, h->stream));
     return 0;
 }
