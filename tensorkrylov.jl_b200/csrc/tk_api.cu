@@ -490,9 +490,9 @@ static double op_bytes_per_row(const tk_handle* h) {
     return h->dk ? acc / h->dk : 0.0;
 }
 
-template <int CPM>
+template <int CPM, int ND>
 static int launch_ttr_t(tk_handle* h, int k, int threads, size_t smem) {
-    auto kernel = lanczos_ttr_kernel<CPM>;
+    auto kernel = lanczos_ttr_kernel<CPM, ND>;
     TK_TRY(allow_smem(kernel, smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(h->dk * CPM);
@@ -526,12 +526,29 @@ static int launch_ttr(tk_handle* h, int k) {
     if (smem > smem_limit(h)) return set_error(TK_EUNSUPPORTED, "n = %d is too large for the 3-term step kernel", h->n);
     int threads = chunk >= 2048 ? 512 : 256;
     if (env_int("TK_TTR_THREADS", 0)) threads = env_int("TK_TTR_THREADS", 0);
-    switch (cpm) {
-        case 1: return launch_ttr_t<1>(h, k, threads, smem);
-        case 2: return launch_ttr_t<2>(h, k, threads, smem);
-        case 4: return launch_ttr_t<4>(h, k, threads, smem);
-        default: return launch_ttr_t<8>(h, k, threads, smem);
+    // all operators DIA with the same small number of diagonals -> kernels with the diagonal loop unrolled
+    int nd = -1;
+    for (int s = 0; s < h->dk && nd != 0; ++s) {
+        const HostOp& o = *h->ops[h->mode_op[s]];
+        const int v = (o.type == OP_DIA && (o.ndiag == 3 || o.ndiag == 4)) ? o.ndiag : 0;
+        nd = (nd == -1 || nd == v) ? v : 0;
     }
+    if (env_int("TK_TTR_GENERIC", 0)) nd = 0;
+#define TK_TTR_CASE(C)                                                        \
+    case C:                                                                   \
+        if (nd == 3) return launch_ttr_t<C, 3>(h, k, threads, smem);          \
+        if (nd == 4) return launch_ttr_t<C, 4>(h, k, threads, smem);          \
+        return launch_ttr_t<C, 0>(h, k, threads, smem);
+    switch (cpm) {
+        TK_TTR_CASE(1)
+        TK_TTR_CASE(2)
+        TK_TTR_CASE(4)
+        default:
+            if (nd == 3) return launch_ttr_t<8, 3>(h, k, threads, smem);
+            if (nd == 4) return launch_ttr_t<8, 4>(h, k, threads, smem);
+            return launch_ttr_t<8, 0>(h, k, threads, smem);
+    }
+#undef TK_TTR_CASE
 }
 
 // Gram row of the newest column for `nmodes` modes starting at local mode `base`

@@ -56,7 +56,19 @@ __device__ __forceinline__ double cluster_sum(double blockval, double* slot) {
     return tot;
 }
 
-template <int CPM>
+// DIA row with a compile-time number of diagonals: lets the compiler unroll and batch the loads of the row loop
+template <int ND>
+__device__ __forceinline__ double apply_row_dia(const OpDesc& op, const double* __restrict__ v, int i, int n) {
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+        const int c = i + op.offs[j];
+        if (c >= 0 && c < n) acc = fma(__ldg(op.diag + (long long)j * op.ld + i), v[c], acc);
+    }
+    return acc;
+}
+
+template <int CPM, int ND>   // ND > 0: every operator is DIA with exactly ND diagonals
 __global__ void __launch_bounds__(512) lanczos_ttr_kernel(KrylovParams p, int k) {
     if (*p.status != ST_RUNNING) return;
     extern __shared__ double smem[];
@@ -75,11 +87,21 @@ __global__ void __launch_bounds__(512) lanczos_ttr_kernel(KrylovParams p, int k)
     const double beta_prev = (k >= 2) ? T[2 * p.ncol + (k - 2)] : 0.0;  // H[k-1,k]  (decompositions.jl:78)
 
     double acc = 0.0;
-    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        double ui = apply_row(op, vk, i, n);
-        if (vkm1) ui -= beta_prev * vkm1[i];
-        u[i - lo] = ui;
-        acc = fma(ui, vk[i], acc);
+    if (ND > 0) {
+#pragma unroll 2
+        for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+            double ui = apply_row_dia<(ND > 0 ? ND : 1)>(op, vk, i, n);
+            if (vkm1) ui -= beta_prev * vkm1[i];
+            u[i - lo] = ui;
+            acc = fma(ui, vk[i], acc);
+        }
+    } else {
+        for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+            double ui = apply_row(op, vk, i, n);
+            if (vkm1) ui -= beta_prev * vkm1[i];
+            u[i - lo] = ui;
+            acc = fma(ui, vk[i], acc);
+        }
     }
     const double alpha = cluster_sum<CPM>(block_sum(acc, scratch), &slots[0]);
 
