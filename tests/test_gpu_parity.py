@@ -583,3 +583,30 @@ def test_large_modes_property(tk, gpu):
     assert bt[0] == pytest.approx(1.0, rel=1e-14) and np.max(np.abs(bt[1:nmax])) < 1e-10
     assert np.all(np.isfinite(cd.relative_residual_norm)) and cd.relative_residual_norm[nmax - 1] < 1e-3
     slv.close()
+
+
+def test_pure_c_client_matches_ctypes_path(tk, gpu, tmp_path):
+    """The C-ABI from C, as a `ccall` wrapper would drive it (tests/c/cabi_demo.c, built with gcc against
+    include/tensorkrylov_b200.h): same histories, bit for bit, as the Python host mirror on the same inputs."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = tmp_path / "cabi_demo"
+    libdir = os.path.dirname(tk.LIB_PATH)
+    subprocess.run(["gcc", "-O1", "-std=c99", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "cabi_demo.c"),
+                    "-o", str(exe), "-L", libdir, "-ltensorkrylov_b200", "-lm", f"-Wl,-rpath,{libdir}"], check=True)
+    d, n, nmax, tol = 7, 300, 20, 1e-8
+    out = subprocess.run([str(exe), tk.TABLES_PATH, str(d), str(n), str(nmax), str(tol)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    status = int(lines[0].split()[1])
+    hist = np.array([[float(x) for x in l.split()[1:]] for l in lines[1:1 + nmax]])
+    b = np.array([0.5 + 0.5 * np.sin(1.0 + 0.37 * i) for i in range(n)])
+    A = tk.KroneckerMatrix.gallery(tk.SymInstance, d, n, tk.Laplace)
+    system = tk.TensorizedSystem(tk.SymInstance, A, [b] * d)
+    cd = tk.solve_tensorized_system(system, nmax, tk.TensorLanczosReorth, tol, verbose=False)
+    assert status == cd.status
+    # b is normalised in C with libm sin / the same operations: allow the last bits of the input to differ
+    assert np.max(np.abs(hist[:, 0] ** 2 - cd.relative_residual_norm ** 2)) <= 4e-11
+    assert np.allclose(hist[1:, 1], cd.projected_residual_norm[1:], rtol=0, atol=4e-11)
+    assert "solution t" in lines[-1]
