@@ -908,6 +908,10 @@ static int reset_state(tk_handle* h) {
     TK_CUDA(cudaMemsetAsync(h->T.p, 0, 8 * h->T.count, h->stream));
     TK_CUDA(cudaMemsetAsync(h->bt.p, 0, 8 * h->bt.count, h->stream));
     TK_CUDA(cudaMemsetAsync(h->detail_d.p, 0, 8 * h->detail_d.count, h->stream));
+    // last-CTA ticket counters: a solve that terminated early may have left kernels half-skipped (every kernel
+    // checks the status word on entry), so the counters are not guaranteed to be back at zero
+    TK_CUDA(cudaMemsetAsync(h->tickets.p, 0, sizeof(unsigned int) * h->tickets.count, h->stream));
+    if (h->ticket_d.p) TK_CUDA(cudaMemsetAsync(h->ticket_d.p, 0, sizeof(unsigned int), h->stream));
     if (h->Hd.p) TK_CUDA(cudaMemsetAsync(h->Hd.p, 0, 8 * h->Hd.count, h->stream));
     TK_CUDA(cudaStreamSynchronize(h->stream));
     h->ev_used = 0;

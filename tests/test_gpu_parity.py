@@ -610,3 +610,28 @@ def test_pure_c_client_matches_ctypes_path(tk, gpu, tmp_path):
     assert np.max(np.abs(hist[:, 0] ** 2 - cd.relative_residual_norm ** 2)) <= 4e-11
     assert np.allclose(hist[1:, 1], cd.projected_residual_norm[1:], rtol=0, atol=4e-11)
     assert "solution t" in lines[-1]
+
+
+def test_handle_reuse_after_early_termination(tk, orc, gpu):
+    """A handle that converged early (kernels of the iterations enqueued ahead were skipped half-way when the status
+    word flipped) must give bit-identical results when it is solved again, and again in fixed-iteration mode."""
+    d, n, nmax = 256, 10000, 40          # config 3 of BASELINE.json: converges at k = 5 for tol 1e-5
+    b = np.random.default_rng(12345).random(n)
+    b /= np.linalg.norm(b)
+    A1 = tk.assemble_matrix(n, tk.Laplace)
+    s = make_solver(tk, [A1] * d, [b] * d, nmax, tk.TensorLanczosReorth, tk.SymInstance, tk.Laplace, tol=1e-5)
+    first = s.solve(1e-5)
+    assert first["status"] in (tk.TK_CONVERGED, tk.TK_BREAKDOWN), "the case must terminate early"
+    assert first["term_k"] < nmax - 8
+    for _ in range(3):
+        again = s.solve(1e-5)
+        assert again["status"] == first["status"] and again["term_k"] == first["term_k"]
+        assert np.array_equal(again["relres"], first["relres"]) and np.array_equal(again["orth"], first["orth"])
+    H0 = s.get_H(0)
+    s.close()
+    fresh = make_solver(tk, [A1] * d, [b] * d, nmax, tk.TensorLanczosReorth, tk.SymInstance, tk.Laplace, tol=1e-5)
+    ref = fresh.solve(1e-5)
+    assert np.array_equal(ref["relres"], first["relres"])
+    k = first["term_k"]
+    assert np.array_equal(fresh.get_H(0)[:k, :k], H0[:k, :k])
+    fresh.close()
