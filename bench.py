@@ -167,6 +167,14 @@ def cpu_arm(a, sample_modes):
     `sample_modes` of the d modes for all nmax-1 iterations.  Per-iteration cost is linear in the number of
     modes, so iterations/s at d modes = (nmax-1) / (t_sample * d / sample_modes)."""
     orc = entry.load_oracle()
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
+    threads = os.cpu_count()
+    try:
+        from threadpoolctl import threadpool_limits, threadpool_info
+        threadpool_limits(limits=threads)
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [threads])
+    except Exception:
+        pass
     tk_tables = os.path.join(entry.PKG_DIR, "data", "expsum_tables.bin")
     tables = orc.ExpSumTables.from_packed(tk_tables)
     ds = min(sample_modes, a.d)
@@ -180,7 +188,6 @@ def cpu_arm(a, sample_modes):
     S.run()
     dt = time.perf_counter() - t0
     its = (a.nmax - 1) / (dt * a.d / ds)
-    threads = os.cpu_count()
     return {"value": its, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{ds} of {a.d} modes x {a.nmax - 1} iterations in {dt:.1f} s, scaled linearly in d; numpy/OpenBLAS "
                       f"with up to {threads} threads; oracle flavour B (GPU-matched algorithm)"}, dt
