@@ -1394,9 +1394,12 @@ int tk_solve(tk_handle* h, double tol, int32_t* status, int64_t* niter, int32_t*
     // Two streams: `stream` advances the Krylov bases (iteration k+1 needs nothing from the compressed solve of
     // iteration k), `stream2` runs eigensolve -> CP assembly -> residual for iteration k as soon as step k is
     // done.  The host polls the device status word LAG iterations behind, so it never stalls the GPU queue.
-    const int LAG = 6, RING = 8;
+    const int RING = 8;
     int st = ST_RUNNING;
     for (int k = 2; k <= h->nmax; ++k) {
+        // how far the enqueue front runs ahead of the last status the host has seen: short while the iterations are
+        // cheap (an early exit then wastes little), longer once the assembly/residual chain has real latency
+        const int LAG = k <= 12 ? 3 : 6;
         if (k - LAG >= 2) {
             const int slot = (k - LAG) % RING;
             TK_CUDA(cudaEventSynchronize(h->ring_ev[slot]));
