@@ -437,13 +437,19 @@ class OracleSolve:
 
     def __init__(self, A_list, b_list, tol, nmax, variant, instance, cls, tables=None,
                  per_mode=False, residual="nilpotent", fast_solve=False, schedule=None,
-                 ignore_breakdown=False):
+                 ignore_breakdown=False, mode_threads=1):
         self.A, self.b = list(A_list), [np.asarray(b, dtype=np.float64) for b in b_list]
         self.d = len(self.A)
         self.n = self.A[0].shape[0]
         self.tol, self.nmax, self.variant, self.instance, self.cls = tol, nmax, variant, instance, cls
         self.per_mode, self.fast_solve = per_mode, fast_solve
         self.ignore_breakdown = ignore_breakdown
+        # the modes are independent inside a Krylov step: a thread pool over modes lets the CPU baseline use every
+        # core (numpy/scipy release the GIL in the matvec, dot and Gram products); results do not depend on it
+        self.pool = None
+        if mode_threads > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            self.pool = ThreadPoolExecutor(max_workers=mode_threads)
         self.residual_fn = residual_faithful if residual == "faithful" else residual_nilpotent
         self.schedule = schedule if schedule is not None else build_schedule(
             self.A[0], self.d, nmax, tol, instance, cls, tables)
@@ -460,10 +466,18 @@ class OracleSolve:
         self.detail = {}
         self.stats = {}
         self.k = 1
-        for s in range(self.d):                                             # :53, orthogonal_bases.jl:142-160
+        def first(s):                                                       # :53, orthogonal_bases.jl:142-160
             self.V[s][:, 0] = (1.0 / np.linalg.norm(self.b[s])) * self.b[s] # initialize_decomp! decompositions.jl:112-118
             self._step(s, 1)
             self.bt[s][0] = self.V[s][:, 0] @ self.b[s]                     # initialize_compressed_rhs utils.jl:456-464
+        self._over_modes(first)
+
+    def _over_modes(self, fn):
+        if self.pool is None:
+            for s in range(self.d):
+                fn(s)
+        else:
+            list(self.pool.map(fn, range(self.d)))
 
     def _step(self, s, k):
         if self.variant == ARNOLDI:
@@ -476,10 +490,10 @@ class OracleSolve:
         k = self.k + 1
         self.k = k
         d = self.d
-        for s in range(d):
+        def advance(s):
             self._step(s, k)                                                # :66
-        for s in range(d):
             self.bt[s][k - 1] = self.V[s][:, k - 1] @ self.b[s]             # update_rhs! :71
+        self._over_modes(advance)
         sc = self.schedule[k]
         Hk = [self.H[s][:k, :k] for s in range(d)]
         btk = [self.bt[s][:k] for s in range(d)]

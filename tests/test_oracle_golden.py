@@ -165,3 +165,13 @@ def test_dense_kronecker_residual_identity(orc, tables):
         x = orc.kruskal_vectorize(S.lastlam, [S.V[s][:, :k] @ S.lastY[s] for s in range(d)])
         true = np.linalg.norm(Ad @ x - bd) / np.linalg.norm(bd)
         assert S.relres[k - 1] == pytest.approx(true, rel=1e-6)
+
+
+def test_oracle_mode_threads_do_not_change_results(orc, tables):
+    """The CPU baseline runs the (independent) modes on a thread pool; the histories are bit-identical."""
+    A = orc.assemble_matrix(300, orc.LAPLACE)
+    b = orc.normalize_rhs(orc.random_rhs(12, 300))
+    r1 = orc.tensorkrylov([A] * 12, b, 1e-8, 12, orc.LANCZOS_REORTH, orc.SYM, orc.LAPLACE, tables, ignore_breakdown=True)
+    r4 = orc.tensorkrylov([A] * 12, b, 1e-8, 12, orc.LANCZOS_REORTH, orc.SYM, orc.LAPLACE, tables, ignore_breakdown=True,
+                          mode_threads=4)
+    assert np.array_equal(r1.relres, r4.relres) and np.array_equal(r1.projres, r4.projres)
