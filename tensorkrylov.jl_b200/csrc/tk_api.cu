@@ -182,6 +182,8 @@ struct HostOp {
     long long nnz = 0;
     DevBuf<double> vals;   // diag / val / dense
     DevBuf<int> rowptr, colidx;
+    bool constd = false;       // DIA with one value per diagonal (Toeplitz): the 3-term kernel needs no operator loads
+    double cval[MAX_DIAG] = {0};
     double norm_bound = 0.0;   // sqrt(||A||_1 ||A||_inf) >= ||A||_2, bounds the squarings of the Hessenberg exponential
     double bytes_per_row() const {  // operator bytes streamed per row by one SpMV
         if (type == OP_DIA) return 8.0 * ndiag;
@@ -325,7 +327,7 @@ struct tk_handle {
         KrylovParams p;
         p.n = n; p.ncol = ncol; p.ldv = ldv; p.vstride = (long long)ncol * ldv;
         p.V = V.p; p.b = b.p; p.T = T.p; p.Hd = Hd.p; p.bt = bt.p; p.g = g.p; p.S = S.p; p.orthS = orthS.p;
-        p.fallbacks = fallbacks.p; p.ops = ops_d.p; p.mode_op = mode_op_d.p; p.status = status_d.p;
+        p.fallbacks = fallbacks.p; p.ops = ops_d.p; p.mode_op = mode_op_d.p; p.status = status_d.p; p.snap = status_d.p + 1;
         p.mode0_local = (first == 0 && dl > 0) ? 0 : -1;
         return p;
     }
@@ -389,6 +391,8 @@ static int upload_ops(tk_handle* h) {
         dsc.val = o.type == OP_CSR ? o.vals.p : nullptr;
         dsc.dense = o.type == OP_DENSE ? o.vals.p : nullptr;
         dsc.rowptr = o.rowptr.p; dsc.colidx = o.colidx.p;
+        dsc.constd = o.constd ? 1 : 0;
+        std::memcpy(dsc.cval, o.cval, sizeof(o.cval));
     }
     TK_TRY(h->ops_d.alloc(std::max<size_t>(descs.size(), 1), false));
     TK_CUDA(cudaMemcpy(h->ops_d.p, descs.data(), descs.size() * sizeof(OpDesc), cudaMemcpyHostToDevice));
@@ -419,10 +423,18 @@ static int alloc_work(tk_handle* h) {
     const int kmax = h->nmax, tmax = std::max(h->tmax, 1);
     const int tld = (tmax + 3) & ~3;
     h->ldq = (h->ncol + 1) & ~1;
-    TK_TRY(h->theta.alloc(tk_handle::NBUF * (size_t)h->ncls * h->ncol));   // ring: eig(k+1..) overlap assembly(k)
-    TK_TRY(h->Q.alloc(tk_handle::NBUF * (size_t)h->ncls * h->ldq * h->ldq));
-    TK_TRY(h->eig_scratch.alloc(tk_handle::NBUF * (size_t)h->ncls * h->ldq * h->ldq, false));
-    TK_TRY(h->eig_need.alloc(tk_handle::NBUF * (size_t)h->ncls));
+    if (!h->use_expm) {
+        // ring: eig(k+1..) overlaps assembly(k).  Q and the bisection scratch are ncls * ldq^2 doubles per slot, so
+        // with per-mode eigenproblems and a large nmax the ring is shortened until it fits in 4 GB
+        h->ring_depth = std::min<int>(tk_handle::NBUF, std::max(1, env_int("TK_RING_DEPTH", tk_handle::NBUF)));
+        const double slot = 2.0 * 8.0 * (double)h->ncls * h->ldq * h->ldq;
+        while (h->ring_depth > 1 && slot * h->ring_depth > 4e9) h->ring_depth >>= 1;
+    }
+    const size_t depth = h->use_expm ? 1 : (size_t)h->ring_depth;
+    TK_TRY(h->theta.alloc(depth * h->ncls * h->ncol));
+    TK_TRY(h->Q.alloc(depth * h->ncls * h->ldq * h->ldq));
+    TK_TRY(h->eig_scratch.alloc(depth * h->ncls * h->ldq * h->ldq, false));
+    TK_TRY(h->eig_need.alloc(depth * h->ncls));
     h->ystride = (long long)kmax * tld;
     TK_TRY(h->Y.alloc((size_t)h->dl * h->ystride));
     TK_TRY(h->Z.alloc((size_t)h->dl * h->ystride));
@@ -510,6 +522,69 @@ static int launch_ttr_t(tk_handle* h, int k, int threads, size_t smem) {
     return 0;
 }
 
+template <int CPM, int ND, bool CONSTD>
+static int launch_ttr_bulk_t(tk_handle* h, int k, int threads, size_t smem) {
+    auto kernel = lanczos_ttr_bulk_kernel<CPM, ND, CONSTD>;
+    TK_TRY(allow_smem(kernel, smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(h->dk * CPM);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CPM; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CPM > 1 ? 1 : 0;
+    KrylovParams p = h->kp();
+    TK_CUDA(cudaLaunchKernelEx(&cfg, kernel, p, k));
+    h->launches++;
+    return 0;
+}
+
+// Bulk-copy 3-term step (lanczos_ttr_bulk_kernel): banded DIA operators with 3 or 4 diagonals inside the halo.
+// Returns 1 when the configuration is not eligible and the generic kernel must run.
+static int launch_ttr_bulk(tk_handle* h, int k, int nd) {
+    if (nd != 3 && nd != 4) return 1;
+    if (!env_int("TK_TTR_BULK", 1)) return 1;
+    bool constd = true;
+    for (int s = 0; s < h->dk; ++s) {
+        const HostOp& o = *h->ops[h->mode_op[s]];
+        for (int j = 0; j < o.ndiag; ++j)
+            if (o.offs[j] < -TTR_HALO || o.offs[j] > TTR_HALO) return 1;
+        constd = constd && o.constd;
+    }
+    if (env_int("TK_TTR_NOCONST", 0)) constd = false;
+    // CTAs per mode: slices of <= 2560 rows (60 KB of shared memory -> 3 CTAs per SM), at least 64 rows each
+    int cpm = 1;
+    while (cpm < 8 && h->n / cpm > 2560) cpm *= 2;
+    while (cpm < 8 && (long long)h->dk * cpm < 296 && h->n / (2 * cpm) >= 512) cpm *= 2;
+    if (env_int("TK_TTR_CPM", 0)) cpm = env_int("TK_TTR_CPM", 0);
+    if (cpm != 1 && cpm != 2 && cpm != 4 && cpm != 8) return 1;
+    const int chunk = (((h->n + cpm - 1) / cpm) + 1) & ~1;
+    if ((long long)(cpm - 1) * chunk >= h->n || chunk < 64) return 1;      // every CTA of a cluster owns rows
+    const size_t smem = ((size_t)3 * chunk + 2 * TTR_HALO) * 8;
+    if (smem > smem_limit(h)) return 1;
+    // every thread keeps TTR_RPT rows of its slice in registers
+    int threads = std::max(64, (((chunk + TTR_RPT - 1) / TTR_RPT) + 31) & ~31);
+    if (env_int("TK_TTR_THREADS", 0)) threads = std::max(threads, env_int("TK_TTR_THREADS", 0));
+    if (threads > 1024) return 1;
+#define TK_BULK_CASE(C)                                                                         \
+    case C:                                                                                     \
+        if (nd == 3) return constd ? launch_ttr_bulk_t<C, 3, true>(h, k, threads, smem)         \
+                                   : launch_ttr_bulk_t<C, 3, false>(h, k, threads, smem);       \
+        return constd ? launch_ttr_bulk_t<C, 4, true>(h, k, threads, smem)                      \
+                      : launch_ttr_bulk_t<C, 4, false>(h, k, threads, smem);
+    switch (cpm) {
+        TK_BULK_CASE(1)
+        TK_BULK_CASE(2)
+        TK_BULK_CASE(4)
+        TK_BULK_CASE(8)
+    }
+#undef TK_BULK_CASE
+    return 1;
+}
+
 static int launch_ttr(tk_handle* h, int k) {
     const double bytes = (op_bytes_per_row(h) + 32.0) * (double)h->n * h->dk;
     TimedScope ts(h, TM_TTR, bytes, h->stream);
@@ -534,6 +609,10 @@ static int launch_ttr(tk_handle* h, int k) {
         nd = (nd == -1 || nd == v) ? v : 0;
     }
     if (env_int("TK_TTR_GENERIC", 0)) nd = 0;
+    {
+        const int rc = launch_ttr_bulk(h, k, nd);
+        if (rc != 1) return rc;
+    }
 #define TK_TTR_CASE(C)                                                        \
     case C:                                                                   \
         if (nd == 3) return launch_ttr_t<C, 3>(h, k, threads, smem);          \
@@ -716,8 +795,9 @@ static CompressParams make_cp(tk_handle* h, int k) {
     CompressParams c;
     c.k = k; c.t = se.t; c.tld = (se.t + 3) & ~3; c.ncol = h->ncol;
     c.per_mode = h->per_mode;
-    c.theta = h->theta.p + (size_t)(k % tk_handle::NBUF) * h->ncls * h->ncol; c.thstride = h->ncol;
-    c.Q = h->Q.p + (size_t)(k % tk_handle::NBUF) * h->ncls * h->ldq * h->ldq; c.qstride = (long long)h->ldq * h->ldq; c.ldq = h->ldq;
+    const size_t eslot = h->use_expm ? 0 : (size_t)(k % h->ring_depth);
+    c.theta = h->theta.p + eslot * h->ncls * h->ncol; c.thstride = h->ncol;
+    c.Q = h->Q.p + eslot * h->ncls * h->ldq * h->ldq; c.qstride = (long long)h->ldq * h->ldq; c.ldq = h->ldq;
     c.bt = h->bt.p;
     c.alpha = h->alpha_d.p + se.off; c.omega = h->omega_d.p + se.off;
     c.lam_inv = 1.0 / se.lambda_min;
@@ -740,7 +820,7 @@ static int enqueue_eig(tk_handle* h, int k) {
     CompressParams c = make_cp(h, k);
     cudaStream_t st = h->stream3[k % tk_handle::NEIG];
     TimedScope ts(h, TM_EIG, 0.0, st);
-    const size_t ring = (size_t)(k % tk_handle::NBUF);
+    const size_t ring = (size_t)(k % h->ring_depth);
     TK_TRY(launch_eig(Tsrc, 3LL * h->ncol, h->ncol, k, h->ncls, const_cast<double*>(c.theta), h->ncol, const_cast<double*>(c.Q),
                       c.qstride, h->ldq, h->status_d.p, h->eigfail_d.p, h->eig_scratch.p + ring * h->ncls * h->ldq * h->ldq,
                       h->eig_need.p + ring * h->ncls, st, &h->launches));
@@ -895,9 +975,9 @@ static int reset_state(tk_handle* h) {
     TK_TRY(upload_ops(h));
     for (int s = 0; s < h->dk; ++s)
         if (!h->rhs_set[s]) return set_error(TK_ESTATE, "right-hand side of mode %d not set", s < h->dl ? h->first + s : 0);
-    const int run = ST_RUNNING, zero = 0;
+    const int run[4] = {ST_RUNNING, ST_RUNNING, ST_RUNNING, 0}, zero = 0;
     const long long nit = h->nmax;
-    TK_CUDA(cudaMemcpyAsync(h->status_d.p, &run, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    TK_CUDA(cudaMemcpyAsync(h->status_d.p, run, sizeof(run), cudaMemcpyHostToDevice, h->stream));
     TK_CUDA(cudaMemcpyAsync(h->term_k_d.p, &zero, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     TK_CUDA(cudaMemcpyAsync(h->eigfail_d.p, &zero, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     TK_CUDA(cudaMemcpyAsync(h->niter_d.p, &nit, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
@@ -1067,7 +1147,7 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
     TK_TRY(h->fallbacks.alloc(dl));
     TK_TRY(h->tickets.alloc(dl));
     TK_TRY(h->mode_op_d.alloc(dl));
-    TK_TRY(h->status_d.alloc(1));
+    TK_TRY(h->status_d.alloc(4));        // [0] live status word, [1..2] snapshots read by the cluster kernels
     TK_TRY(h->term_k_d.alloc(1));
     TK_TRY(h->eigfail_d.alloc(1));
     TK_TRY(h->niter_d.alloc(1));
@@ -1180,6 +1260,13 @@ int tk_set_operator_csc(tk_handle* h, int32_t s, int64_t n, const int64_t* colpt
                 const int64_t i = rowval[p] - 1;
                 diag[(size_t)idx[j - i] * n + i] += nzval[p];
             }
+        op->constd = true;
+        for (int j = 0; j < op->ndiag && op->constd; ++j) {
+            const long long o = op->offs[j], i0 = std::max(0LL, -o), i1 = std::min<long long>(n, n - o);
+            op->cval[j] = i0 < i1 ? diag[(size_t)j * n + i0] : 0.0;
+            for (long long i = i0; i < i1; ++i)
+                if (std::memcmp(&diag[(size_t)j * n + i], &op->cval[j], 8) != 0) { op->constd = false; break; }
+        }
         TK_TRY(op->vals.alloc(diag.size(), false));
         TK_CUDA(cudaMemcpy(op->vals.p, diag.data(), 8 * diag.size(), cudaMemcpyHostToDevice));
     } else {
@@ -1590,7 +1677,7 @@ int tk_get_eig(tk_handle* h, int32_t s, int32_t k, double* theta, double* Q) {
     if (!local) return set_error(TK_EINVAL, "mode %d is owned by another rank", s);
     TK_CUDA(cudaSetDevice(h->device));
     const int cls = h->per_mode ? s - h->first : 0;
-    const size_t par = (size_t)(k % tk_handle::NBUF);
+    const size_t par = h->use_expm ? 0 : (size_t)(k % h->ring_depth);
     if (theta) TK_CUDA(cudaMemcpy(theta, h->theta.p + (par * h->ncls + cls) * h->ncol, 8 * (size_t)k, cudaMemcpyDeviceToHost));
     if (Q) {
         std::vector<double> q((size_t)h->ldq * k);

@@ -29,6 +29,8 @@ struct OpDesc {
     const int* colidx;
     const double* val;
     const double* dense;
+    int constd;               // DIA: every diagonal holds one value on its in-matrix part ...
+    double cval[MAX_DIAG];    // ... which is cval[j] (Toeplitz operators like the 1D Laplacian)
 };
 
 // Krylov state of the modes this GPU owns.  k is the reference's 1-based iteration:
@@ -50,6 +52,7 @@ struct KrylovParams {
     const OpDesc* ops;
     const int* mode_op;  // [dl]
     const int* status;   // device status word
+    int* snap;           // [2] launch-uniform snapshots of the status word for the cluster kernels
     int mode0_local;     // local index of global mode 0, or -1 if another rank owns it
 };
 

@@ -44,6 +44,16 @@ __global__ void __launch_bounds__(512) init_basis_kernel(KrylovParams p, double*
 //   v_{k+1} = v^ / beta (zeros if beta == 0);  H[k+1,k] = H[k,k+1] = beta;  b~[k+1] = v_{k+1}.b = (v^.b)/beta
 // Algorithmic HBM bytes per mode: (ndiag + 4) * 8 * n  (diagonals, v_k, v_{k-1}, b read; v_{k+1} written).
 // ------------------------------------------------------------------------------------------
+// The status word is flipped by finalize_kernel on another stream while 3-term steps of later iterations are in
+// flight.  The CTAs of a cluster exchange partial sums through each other's shared memory, so all of them must take
+// the same run/skip decision: they read a snapshot that only the 3-term kernels themselves write (launch k reads
+// slot k&1 and refreshes slot (k+1)&1 for the next launch on the same stream), never the live word.
+__device__ __forceinline__ bool ttr_running(const KrylovParams& p, int k) {
+    const int st = p.snap[k & 1];
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.snap[(k + 1) & 1] = (st != ST_RUNNING) ? st : *p.status;
+    return st == ST_RUNNING;
+}
+
 template <int CPM>
 __device__ __forceinline__ double cluster_sum(double blockval, double* slot) {
     if (CPM == 1) return blockval;
@@ -70,7 +80,7 @@ __device__ __forceinline__ double apply_row_dia(const OpDesc& op, const double* 
 
 template <int CPM, int ND>   // ND > 0: every operator is DIA with exactly ND diagonals
 __global__ void __launch_bounds__(512) lanczos_ttr_kernel(KrylovParams p, int k) {
-    if (*p.status != ST_RUNNING) return;
+    if (!ttr_running(p, k)) return;
     extern __shared__ double smem[];
     __shared__ double scratch[64];
     __shared__ double slots[4];
@@ -140,6 +150,146 @@ __global__ void __launch_bounds__(512) lanczos_ttr_kernel(KrylovParams p, int k)
         p.bt[(long long)s * p.ncol + k] = btn;
     }
     if (CPM > 1) cg::this_cluster().sync();  // keep every CTA's slots alive until all peers have read them
+}
+
+// ------------------------------------------------------------------------------------------
+// Bulk-copy variant of the 3-term step for banded operators (DIA, every |offset| <= TTR_HALO).
+// The slices of v_k (with a halo), v_{k-1} and b a CTA needs are fetched by three cp.async.bulk copies that
+// complete on one mbarrier, so a CTA has its whole input (24 bytes per row) in flight from its first
+// instruction without holding registers for it; the three passes then run out of shared memory and the only
+// global traffic left in them is the diagonals (L2-resident, or none at all when every diagonal is constant:
+// CONSTD) and the store of v_{k+1}.  Same thread-to-row map and reduction order as lanczos_ttr_kernel, so for
+// equal (CPM, blockDim) the two kernels give bit-identical results.
+// ------------------------------------------------------------------------------------------
+constexpr int TTR_HALO = 2;   // doubles on each side of the v_k slice: keeps every copy 16-byte aligned
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+// Wait for phase `parity` of an mbarrier; traps instead of hanging if the copies never land.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_addr(bar);
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (done) return;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+
+constexpr int TTR_RPT = 10;   // rows per thread of the bulk kernel (its u / v^ slice lives in registers)
+
+template <int CPM, int ND, bool CONSTD>
+__global__ void __launch_bounds__(1024) lanczos_ttr_bulk_kernel(KrylovParams p, int k) {
+    if (!ttr_running(p, k)) return;
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double scratch[64];
+    __shared__ double slots[2 + 2 * CPM];                     // [0] alpha partial (pulled), [2+2r..] partials pushed by rank r
+    __shared__ __align__(8) uint64_t bar;
+    const int s = blockIdx.x / CPM, part = blockIdx.x % CPM, n = p.n;
+    const int chunk = (((n + CPM - 1) / CPM) + 1) & ~1;
+    const int lo = part * chunk, hi = min(n, lo + chunk);     // host guarantees lo < n for every part
+    const double* vks = smem + TTR_HALO;                      // row i of v_k at vks[i - lo]
+    const double* us = smem + chunk + 2 * TTR_HALO;           // v_{k-1} slice
+    const double* bs = us + chunk;
+    const OpDesc& op = p.ops[p.mode_op[s]];
+    double* Vs = p.V + (long long)s * p.vstride;
+    const double* vk = Vs + (long long)(k - 1) * p.ldv;
+    const double* vkm1 = (k >= 2) ? Vs + (long long)(k - 2) * p.ldv : nullptr;
+    const double* b = p.b + (long long)s * p.ldv;
+    double* vnew = Vs + (long long)k * p.ldv;
+    double* T = p.T + (long long)s * 3 * p.ncol;
+
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_addr(&bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // ranges in rows, even at both ends (ldv is a multiple of 16 and columns are padded up to it)
+        const int he = (int)min((long long)((hi + 1) & ~1), p.ldv);
+        const int g0 = max(lo - TTR_HALO, 0), g1 = (int)min((long long)he + TTR_HALO, p.ldv);
+        const uint32_t bytes_v = (uint32_t)(g1 - g0) * 8u, bytes_s = (uint32_t)(he - lo) * 8u;
+        const uint32_t total = bytes_v + bytes_s * (vkm1 ? 2u : 1u);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(&bar)), "r"(total) : "memory");
+        bulk_load(smem + (g0 - lo + TTR_HALO), vk + g0, bytes_v, &bar);
+        if (vkm1) bulk_load(smem + chunk + 2 * TTR_HALO, vkm1 + lo, bytes_s, &bar);
+        bulk_load(smem + 2 * chunk + 2 * TTR_HALO, b + lo, bytes_s, &bar);
+    }
+    int offs[ND];
+    double cval[ND];
+#pragma unroll
+    for (int j = 0; j < ND; ++j) { offs[j] = op.offs[j]; cval[j] = CONSTD ? op.cval[j] : 0.0; }
+    const double beta_prev = (k >= 2) ? T[2 * p.ncol + (k - 2)] : 0.0;  // H[k-1,k]  (decompositions.jl:78)
+    __syncthreads();                                          // the barrier is initialised before anyone polls it
+    mbar_wait(&bar, 0);
+
+    // u = A v_k - beta_{k-1} v_{k-1} for rows lo + threadIdx.x + r * blockDim.x, kept in registers
+    double u[TTR_RPT];
+    double acc = 0.0;
+#pragma unroll
+    for (int r = 0; r < TTR_RPT; ++r) {
+        const int li = threadIdx.x + r * blockDim.x, i = lo + li;
+        double ui = 0.0;
+        if (i < hi) {
+#pragma unroll
+            for (int j = 0; j < ND; ++j) {
+                const int c = i + offs[j];
+                if ((unsigned)c < (unsigned)n)
+                    ui = fma(CONSTD ? cval[j] : __ldg(op.diag + (long long)j * op.ld + i), vks[li + offs[j]], ui);
+            }
+            if (vkm1) ui -= beta_prev * us[li];
+            acc = fma(ui, vks[li], acc);
+        }
+        u[r] = ui;
+    }
+    const double alpha = cluster_sum<CPM>(block_sum(acc, scratch), &slots[0]);
+
+    double accb = 0.0;
+    acc = 0.0;
+#pragma unroll
+    for (int r = 0; r < TTR_RPT; ++r) {
+        const int li = threadIdx.x + r * blockDim.x;
+        if (lo + li < hi) {
+            const double w = u[r] - alpha * vks[li];
+            u[r] = w;
+            acc = fma(w, w, acc);
+            accb = fma(w, bs[li], accb);
+        }
+    }
+    block_sum2(acc, accb, scratch);
+    double beta2 = acc, vb = accb;
+    if (CPM > 1) {
+        // push the two partials into every CTA of the cluster; after the barrier each CTA only reads its own
+        // shared memory, so no CTA can exit while a peer still needs it
+        cg::cluster_group cl = cg::this_cluster();
+        if (threadIdx.x < CPM) {
+            double* dst = cl.map_shared_rank(slots, threadIdx.x) + 2 + 2 * part;
+            dst[0] = acc; dst[1] = accb;
+        }
+        cl.sync();
+        beta2 = 0.0; vb = 0.0;
+#pragma unroll
+        for (int r = 0; r < CPM; ++r) { beta2 += slots[2 + 2 * r]; vb += slots[3 + 2 * r]; }
+    }
+    const double beta = sqrt(beta2);
+    const double inv = (beta == 0.0) ? 0.0 : 1.0 / beta;
+#pragma unroll
+    for (int r = 0; r < TTR_RPT; ++r) {
+        const int li = threadIdx.x + r * blockDim.x;
+        if (lo + li < hi) vnew[lo + li] = inv * u[r];
+    }
+    const double btn = inv * vb;
+    if (part == 0 && threadIdx.x == 0) {
+        T[k - 1] = alpha;                   // H[k,k]
+        T[p.ncol + (k - 1)] = beta;         // H[k+1,k]
+        T[2 * p.ncol + (k - 1)] = beta;     // H[k,k+1]   update_subdiagonals!, decompositions.jl:180-186
+        p.bt[(long long)s * p.ncol + k] = btn;
+    }
 }
 
 // ------------------------------------------------------------------------------------------

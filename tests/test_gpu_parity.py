@@ -635,3 +635,28 @@ def test_handle_reuse_after_early_termination(tk, orc, gpu):
     k = first["term_k"]
     assert np.array_equal(fresh.get_H(0)[:k, :k], H0[:k, :k])
     fresh.close()
+
+
+@pytest.mark.parametrize("depth", [1, 2])
+def test_short_spectral_ring_gives_identical_histories(tk, orc, gpu, monkeypatch, depth):
+    """The eigensolves run up to ring_depth iterations ahead of the assembly.  With per-mode eigenproblems and a large
+    nmax the library shortens that ring to bound memory (tk_api.cu alloc_work); TK_RING_DEPTH forces the short ring
+    here.  The histories must not depend on the depth, bit for bit."""
+    d, n, nmax = 6, 300, 40
+    rng = np.random.default_rng(77)
+    A1 = tk.assemble_matrix(n, tk.Laplace)
+    b = orc.normalize_rhs([rng.random(n) for _ in range(d)])
+
+    def run():
+        s = make_solver(tk, [A1] * d, b, nmax, tk.TensorLanczosReorth, tk.SymInstance, tk.Laplace,
+                        flags=tk.TK_FLAG_FIXED_ITERATIONS)      # no REFERENCE_H1: one eigenproblem per mode
+        out = s.solve(1e-8)
+        s.close()
+        return out
+
+    full = run()
+    monkeypatch.setenv("TK_RING_DEPTH", str(depth))
+    short = run()
+    for key in ("relres", "projres", "orth"):
+        assert np.array_equal(full[key], short[key]), key
+    assert full["status"] == short["status"] and full["term_k"] == short["term_k"]
