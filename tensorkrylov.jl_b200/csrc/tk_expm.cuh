@@ -171,11 +171,24 @@ __global__ void __launch_bounds__(256) expm_fused_kernel(ExpmParams p, double f0
                                                          double f4, double f5, double f6, double f7, double f8, double f9,
                                                          double f10, double f11, double f12, double f13, double f14,
                                                          double f15, double f16) {
-    if (*p.status != ST_RUNNING) return;
+    constexpr int CL = TILES * TILES;
+    if (CL > 1) {
+        // The status word can flip (finalize_kernel, another stream) while this launch is starting.  The CTAs of a
+        // cluster meet at cluster barriers, so they must all take the same run/skip decision: CTA 0 of the cluster
+        // reads the word and the others take its copy through distributed shared memory.
+        __shared__ int st_sh;
+        cg::cluster_group cl = cg::this_cluster();
+        if (cl.block_rank() == 0 && threadIdx.x == 0) st_sh = *p.status;
+        cl.sync();
+        const int st = *cl.map_shared_rank(&st_sh, 0);
+        cl.sync();                       // CTA 0 keeps its copy alive until every peer has read it
+        if (st != ST_RUNNING) return;
+    } else if (*p.status != ST_RUNNING) {
+        return;
+    }
     __shared__ double As[16][65];
     __shared__ double Bs[16][65];
     __shared__ double scratch[32];
-    constexpr int CL = TILES * TILES;
     const int m = blockIdx.x / CL, ct = blockIdx.x % CL;
     const int row0 = (ct / TILES) * 64, col0 = (ct % TILES) * 64;
     const int c = m / p.t, j = m % p.t, k = p.k, ld = p.ld;

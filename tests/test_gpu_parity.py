@@ -660,3 +660,28 @@ def test_short_spectral_ring_gives_identical_histories(tk, orc, gpu, monkeypatch
     for key in ("relres", "projres", "orth"):
         assert np.array_equal(full[key], short[key]), key
     assert full["status"] == short["status"] and full["term_k"] == short["term_k"]
+
+
+def test_nonsym_early_termination_beyond_64_columns(tk, orc, gpu):
+    """A NonSymInstance solve that terminates at k > 64, where the exponentials run as clusters of 4 CTAs per matrix
+    and several iterations are in flight when the status word flips: the CTAs of a cluster must agree on running or
+    skipping.  The terminated solve must stop at the first k below the tolerance and be repeatable."""
+    d, n, nmax = 2, 200, 110
+    rng = np.random.default_rng(3)
+    b = orc.normalize_rhs([rng.random(n)] * d)
+    A = tk.assemble_matrix(n, tk.Laplace)      # as a NonSymInstance the residual starts falling at k ~ 75
+    fixed = make_solver(tk, [A] * d, b, nmax, tk.TensorArnoldi, tk.NonSymInstance, tk.Laplace, tol=1e-6,
+                        flags=tk.TK_FLAG_REFERENCE_H1 | tk.TK_FLAG_FIXED_ITERATIONS)
+    hist = fixed.solve(1e-6)["relres"]
+    fixed.close()
+    # first record low at an iteration in the 4-CTA-cluster range (reference k is 1-based: entry k-1)
+    kstar = next((k for k in range(68, nmax) if hist[k - 1] < 0.99 * hist[1:k - 1].min()), None)
+    if kstar is None:
+        pytest.skip("history has no record low beyond k = 68")
+    tol = 0.5 * (hist[kstar - 1] + hist[1:kstar - 1].min())
+    s = make_solver(tk, [A] * d, b, nmax, tk.TensorArnoldi, tk.NonSymInstance, tk.Laplace, tol=1e-6)
+    for _ in range(4):
+        out = s.solve(tol)
+        assert out["status"] == tk.TK_CONVERGED and out["term_k"] == kstar
+        assert np.array_equal(out["relres"][:kstar], hist[:kstar])
+    s.close()
