@@ -353,7 +353,10 @@ def run_b200(a):
     e2e_ms = maxr(1e3 * (time.perf_counter() - t0))
     assert abs(cd.relative_residual_norm[nmax - 1] - relres_last) <= 1e-9 * abs(relres_last) + 1e-300
     dl = slv.count
-    h2d = dl * n * 8 + 3 * n * 8 + sum(16 * 64 for _ in range(nmax))
+    # bytes that actually cross PCIe per call: the reference aliases ONE rhs vector and ONE matrix over all d modes
+    # (system.jl:5-11, tensor_struct.jl:208-210) and the library honours that (tk_set_rhs_all, tk_share_operator):
+    # b once, the CSC arrays of A_1 once (colptr, rowval, nzval), the exp-sum schedule (<= 64 terms per iteration)
+    h2d = n * 8 + (n + 1) * 8 + 2 * int(A1.nnz) * 8 + sum(16 * 64 for _ in range(nmax))
     d2h = 3 * nmax * 8 + 64
 
     if rank != 0:

@@ -112,6 +112,9 @@ int tk_set_operator_csc(tk_handle* h, int32_t s, int64_t n, const int64_t* colpt
 int tk_set_operator_dense(tk_handle* h, int32_t s, int64_t n, const double* a, char uplo);
 /* the reference aliases one matrix object d times (tensor_struct.jl:208-210) */
 int tk_share_operator(tk_handle* h, int32_t s_dst, int32_t s_src);
+/* the same for every mode this rank holds at once: KroneckerMatrix{U}(A_1, d) fills all d slots with one object
+   (tensor_struct.jl:208-210); one call instead of d - 1 */
+int tk_share_operator_all(tk_handle* h, int32_t s_src);
 /* b_s as handed to tensorkrylov! (already normalised by TensorizedSystem, system.jl:33-37) */
 int tk_set_rhs(tk_handle* h, int32_t s, const double* b, int64_t n);
 /* one vector for all local modes: random_rhs, system.jl:5-11 */

@@ -27,7 +27,7 @@ EXPORTS = [
     "tk_last_error", "tk_version", "tk_device_count",
     "tk_tables_load", "tk_tables_sym_lookup", "tk_nonsym_coefficients", "tk_laplace_extremes",
     "tk_comm_unique_id", "tk_create", "tk_destroy", "tk_release_cache", "tk_local_modes", "tk_needs_mode",
-    "tk_set_operator_csc", "tk_set_operator_dense", "tk_share_operator", "tk_set_rhs", "tk_set_rhs_all",
+    "tk_set_operator_csc", "tk_set_operator_dense", "tk_share_operator", "tk_share_operator_all", "tk_set_rhs", "tk_set_rhs_all",
     "tk_set_schedule", "tk_schedule_laplace", "tk_solve", "tk_solution_rank", "tk_get_solution", "tk_get_solution_all",
     "tk_begin", "tk_step_bases", "tk_compress", "tk_residual",
     "tk_get_H", "tk_get_V", "tk_get_bt", "tk_get_Y", "tk_get_eig", "tk_get_orth_state",
@@ -67,6 +67,7 @@ def _load():
         "tk_set_operator_csc": (C.c_int, [p, i32, i64, pi64, pi64, pd]),
         "tk_set_operator_dense": (C.c_int, [p, i32, i64, pd, C.c_char]),
         "tk_share_operator": (C.c_int, [p, i32, i32]),
+        "tk_share_operator_all": (C.c_int, [p, i32]),
         "tk_set_rhs": (C.c_int, [p, i32, pd, i64]),
         "tk_set_rhs_all": (C.c_int, [p, pd, i64]),
         "tk_set_schedule": (C.c_int, [p, i32, f64, i32, pd, pd]),

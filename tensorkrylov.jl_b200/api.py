@@ -226,8 +226,12 @@ class Solver:
     # inputs
     def set_operators(self, M):
         seen = {}
+        one = bool(self.fed) and all(M[s] is M[self.fed[0]] for s in self.fed)
         for s in self.fed:
             A = M[s]
+            if one and seen:          # one matrix object in every slot (tensor_struct.jl:208-210)
+                check(lib.tk_share_operator_all(self.h, self.fed[0]))
+                return
             if id(A) in seen:
                 check(lib.tk_share_operator(self.h, s, seen[id(A)]))
                 continue

@@ -522,9 +522,9 @@ static int launch_ttr_t(tk_handle* h, int k, int threads, size_t smem) {
     return 0;
 }
 
-template <int CPM, int ND, bool CONSTD>
+template <int CPM, int ND, bool CONSTD, int RPT>
 static int launch_ttr_bulk_t(tk_handle* h, int k, int threads, size_t smem) {
-    auto kernel = lanczos_ttr_bulk_kernel<CPM, ND, CONSTD>;
+    auto kernel = lanczos_ttr_bulk_kernel<CPM, ND, CONSTD, RPT>;
     TK_TRY(allow_smem(kernel, smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(h->dk * CPM);
@@ -565,16 +565,16 @@ static int launch_ttr_bulk(tk_handle* h, int k, int nd) {
     if ((long long)(cpm - 1) * chunk >= h->n || chunk < 64) return 1;      // every CTA of a cluster owns rows
     const size_t smem = ((size_t)3 * chunk + 2 * TTR_HALO) * 8;
     if (smem > smem_limit(h)) return 1;
-    // every thread keeps TTR_RPT rows of its slice in registers
+    // every thread keeps TTR_RPT rows of its slice in registers (5 and 20 rows per thread measured slower)
     int threads = std::max(64, (((chunk + TTR_RPT - 1) / TTR_RPT) + 31) & ~31);
     if (env_int("TK_TTR_THREADS", 0)) threads = std::max(threads, env_int("TK_TTR_THREADS", 0));
-    if (threads > 1024) return 1;
-#define TK_BULK_CASE(C)                                                                         \
-    case C:                                                                                     \
-        if (nd == 3) return constd ? launch_ttr_bulk_t<C, 3, true>(h, k, threads, smem)         \
-                                   : launch_ttr_bulk_t<C, 3, false>(h, k, threads, smem);       \
-        return constd ? launch_ttr_bulk_t<C, 4, true>(h, k, threads, smem)                      \
-                      : launch_ttr_bulk_t<C, 4, false>(h, k, threads, smem);
+    if (threads > 512) return 1;
+#define TK_BULK_CASE(C)                                                                                  \
+    case C:                                                                                              \
+        if (nd == 3) return constd ? launch_ttr_bulk_t<C, 3, true, TTR_RPT>(h, k, threads, smem)         \
+                                   : launch_ttr_bulk_t<C, 3, false, TTR_RPT>(h, k, threads, smem);       \
+        return constd ? launch_ttr_bulk_t<C, 4, true, TTR_RPT>(h, k, threads, smem)                      \
+                      : launch_ttr_bulk_t<C, 4, false, TTR_RPT>(h, k, threads, smem);
     switch (cpm) {
         TK_BULK_CASE(1)
         TK_BULK_CASE(2)
@@ -1351,6 +1351,18 @@ int tk_share_operator(tk_handle* h, int32_t s_dst, int32_t s_src) {
     if (ns == 0) return set_error(TK_EINVAL, "mode %d is not held by this rank; set its operator here first", s_src);
     if (h->mode_op[src[0]] < 0) return set_error(TK_ESTATE, "operator of mode %d not set", s_src);
     for (int i = 0; i < nd; ++i) h->mode_op[dst[i]] = h->mode_op[src[0]];
+    h->ops_dirty = true;
+    return 0;
+}
+
+int tk_share_operator_all(tk_handle* h, int32_t s_src) {
+    bool ls = false;
+    TK_TRY(check_mode(h, s_src, &ls));
+    int src[2];
+    if (slots_of(h, s_src, src) == 0)
+        return set_error(TK_EINVAL, "mode %d is not held by this rank; set its operator here first", s_src);
+    if (h->mode_op[src[0]] < 0) return set_error(TK_ESTATE, "operator of mode %d not set", s_src);
+    std::fill(h->mode_op.begin(), h->mode_op.begin() + h->dk, h->mode_op[src[0]]);
     h->ops_dirty = true;
     return 0;
 }

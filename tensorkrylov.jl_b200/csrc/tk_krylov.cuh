@@ -185,9 +185,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 constexpr int TTR_RPT = 10;   // rows per thread of the bulk kernel (its u / v^ slice lives in registers)
 
-template <int CPM, int ND, bool CONSTD>
-__global__ void __launch_bounds__(1024) lanczos_ttr_bulk_kernel(KrylovParams p, int k) {
-    if (!ttr_running(p, k)) return;
+template <int CPM, int ND, bool CONSTD, int RPT>
+__global__ void __launch_bounds__(512) lanczos_ttr_bulk_kernel(KrylovParams p, int k) {
+    // the snapshot is only consumed after the bulk loads have been issued (and have landed): its latency is off the
+    // critical path, and a skipped launch merely fetches three slices it does not use
+    const bool running = ttr_running(p, k);
     extern __shared__ __align__(16) double smem[];
     __shared__ double scratch[64];
     __shared__ double slots[2 + 2 * CPM];                     // [0] alpha partial (pulled), [2+2r..] partials pushed by rank r
@@ -227,12 +229,13 @@ __global__ void __launch_bounds__(1024) lanczos_ttr_bulk_kernel(KrylovParams p, 
     const double beta_prev = (k >= 2) ? T[2 * p.ncol + (k - 2)] : 0.0;  // H[k-1,k]  (decompositions.jl:78)
     __syncthreads();                                          // the barrier is initialised before anyone polls it
     mbar_wait(&bar, 0);
+    if (!running) return;
 
     // u = A v_k - beta_{k-1} v_{k-1} for rows lo + threadIdx.x + r * blockDim.x, kept in registers
-    double u[TTR_RPT];
+    double u[RPT];
     double acc = 0.0;
 #pragma unroll
-    for (int r = 0; r < TTR_RPT; ++r) {
+    for (int r = 0; r < RPT; ++r) {
         const int li = threadIdx.x + r * blockDim.x, i = lo + li;
         double ui = 0.0;
         if (i < hi) {
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(1024) lanczos_ttr_bulk_kernel(KrylovParams p, 
     double accb = 0.0;
     acc = 0.0;
 #pragma unroll
-    for (int r = 0; r < TTR_RPT; ++r) {
+    for (int r = 0; r < RPT; ++r) {
         const int li = threadIdx.x + r * blockDim.x;
         if (lo + li < hi) {
             const double w = u[r] - alpha * vks[li];
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(1024) lanczos_ttr_bulk_kernel(KrylovParams p, 
     const double beta = sqrt(beta2);
     const double inv = (beta == 0.0) ? 0.0 : 1.0 / beta;
 #pragma unroll
-    for (int r = 0; r < TTR_RPT; ++r) {
+    for (int r = 0; r < RPT; ++r) {
         const int li = threadIdx.x + r * blockDim.x;
         if (lo + li < hi) vnew[lo + li] = inv * u[r];
     }

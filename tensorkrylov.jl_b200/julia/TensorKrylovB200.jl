@@ -64,12 +64,17 @@ function tensorkrylov_b200!(convergence_data::ConvergenceData{T}, A::KronMat{mat
     try
         # operators: the reference aliases one matrix object d times (tensor_struct.jl:208-210)
         first_of = IdDict{Any, Int}()
+        if all(A[s] === A[1] for s in 2:d)
+            set_operator!(h, 1, A[1])
+            check(ccall((:tk_share_operator_all, libtk), Cint, (Ptr{Cvoid}, Int32), h, 0))
+        else
         for s in 1:d
             if haskey(first_of, A[s])
                 check(ccall((:tk_share_operator, libtk), Cint, (Ptr{Cvoid}, Int32, Int32), h, s - 1, first_of[A[s]] - 1))
             else
                 set_operator!(h, s, A[s]); first_of[A[s]] = s
             end
+        end
         end
         for s in 1:d
             check(ccall((:tk_set_rhs, libtk), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64), h, s - 1, b[s], length(b[s])))

@@ -1,7 +1,7 @@
 #!/bin/bash
-# developer tool: 3-term step, bulk-copy kernel vs the load/store kernel, cluster width and CTA size (C5, one GPU)
+# developer tool: 3-term step, bulk-copy kernel vs the load/store kernel, cluster width (C5, one GPU)
 D=${1:-1024}
-for cfg in "TK_TTR_BULK=0" "TK_TTR_BULK=1" "TK_TTR_NOCONST=1" "TK_TTR_THREADS=256" "TK_TTR_CPM=4" "TK_TTR_CPM=4 TK_TTR_THREADS=512"; do
+for cfg in "TK_TTR_BULK=0" "TK_TTR_BULK=1" "TK_TTR_CPM=2" "TK_TTR_CPM=8" "TK_TTR_NOCONST=1"; do
   echo "== d=$D $cfg"
   env $cfg timeout 300 python tools/profile_phases.py $D 10000 64 reorth | python -c "import json,sys; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('ttr','gram','solve','relres_last')})"
 done
