@@ -408,7 +408,7 @@ constexpr int ASM_TJ = 16;
 
 __device__ void gram_blocks_body(const CompressParams& p, double* scratch);
 
-__global__ void __launch_bounds__(256) assemble_cp_kernel(CompressParams p) {
+__global__ void __launch_bounds__(256, 3) assemble_cp_kernel(CompressParams p) {
     if (*p.status != ST_RUNNING) return;
     extern __shared__ double smem[];
     const int s = blockIdx.x, k = p.k, t = p.t;
