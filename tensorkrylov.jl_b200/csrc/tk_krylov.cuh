@@ -2,6 +2,7 @@
 //
 //   init_basis_kernel     V[:,1] = b/||b||, b~[1]                (decompositions.jl:112-118, utils.jl:456-464)
 //   lanczos_ttr_kernel    3-term recurrence step                (orthogonal_bases.jl:39-67)
+//   lanczos_ttr_bulk_kernel   the same step for banded operators, inputs fetched by cp.async.bulk (TMA)
 //   gram_row_kernel       g_j = v_j . v_{k+1}, j = 1..k+1       (the only NEW row of V'V; orthogonal_bases.jl:119,250-257)
 //   monitor_body          loss test + MGS fallback, run by the last gram_row CTA of a mode (orthogonal_bases.jl:119-131)
 //   arnoldi_mgs_kernel    two-pass modified Gram-Schmidt step   (orthogonal_bases.jl:15-37)

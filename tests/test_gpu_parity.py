@@ -685,3 +685,32 @@ def test_nonsym_early_termination_beyond_64_columns(tk, orc, gpu):
         assert out["status"] == tk.TK_CONVERGED and out["term_k"] == kstar
         assert np.array_equal(out["relres"][:kstar], hist[:kstar])
     s.close()
+
+
+@pytest.mark.parametrize("n,cpm", [(1000, 1), (1001, 2), (4000, 4)])
+def test_bulk_copy_ttr_kernel_is_bit_identical_to_the_plain_kernel(tk, orc, gpu, monkeypatch, n, cpm):
+    """lanczos_ttr_bulk_kernel (cp.async.bulk + mbarrier, register-resident u, Toeplitz coefficients from the
+    descriptor) and lanczos_ttr_kernel (plain loads, u in shared memory) use the same thread-to-row map and the same
+    reduction order: with equal cluster width and CTA size every basis vector and every entry of H must agree bit
+    for bit -- odd n (padded slices), one CTA per mode and clusters of 2 and 4."""
+    d, nmax = 3, 30
+    rng = np.random.default_rng(n)
+    A = tk.assemble_matrix(n, tk.Laplace)
+    b = orc.normalize_rhs([rng.random(n) for _ in range(d)])
+    monkeypatch.setenv("TK_TTR_CPM", str(cpm))
+    monkeypatch.setenv("TK_TTR_THREADS", "256")
+
+    def bases(bulk):
+        monkeypatch.setenv("TK_TTR_BULK", "1" if bulk else "0")
+        s = make_solver(tk, [A] * d, b, nmax, tk.TensorLanczos, tk.SymInstance, tk.Laplace)
+        s.begin()
+        for k in range(2, nmax + 1):
+            s.step_bases(k)
+        out = [(s.get_H(m), s.get_V(m, nmax + 1), s.get_bt(m)) for m in range(d)]
+        s.close()
+        return out
+
+    for (Ha, Va, ba), (Hb, Vb, bb) in zip(bases(True), bases(False)):
+        assert np.array_equal(Ha, Hb)
+        assert np.array_equal(Va, Vb)
+        assert np.array_equal(ba, bb)
