@@ -52,7 +52,8 @@ def parse():
 
 
 def workload_name(a):
-    return (f"C5 d={a.d} n={a.n} Laplace TensorLanczos{'Reorth' if a.variant == 'reorth' else ''} nmax={a.nmax} "
+    tag = "C5" if (a.d, a.n, a.nmax) == (1024, 10000, 64) else "custom"
+    return (f"{tag} d={a.d} n={a.n} Laplace TensorLanczos{'Reorth' if a.variant == 'reorth' else ''} nmax={a.nmax} "
             f"tol={a.tol:g} fixed-iterations {'per-mode H_s' if a.per_mode else 'reference H_1'}")
 
 

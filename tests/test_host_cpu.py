@@ -198,3 +198,36 @@ def test_mode_sharding_and_partial_merge_world2_gloo(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert f"rank {r} ok" in o
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm) needs no GPU: one JSON line with
+    the contract's keys, the oracle port as the thing timed."""
+    import json, subprocess, sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--d", "16", "--n", "500", "--nmax", "12", "--cpu-sample-modes", "8"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "krylov_iters_per_s" and d["unit"] == "iter/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_committed_ncu_launch_list_matches_its_summary():
+    """profiles/: the launch list of one timed solve holds 445 launches (7 per iteration + init + the QL check) and the
+    per-kernel totals in the summary are the sums of its rows."""
+    import collections, csv, re
+    rows = [r for r in csv.reader(open(os.path.join(ROOT, "profiles", "r01_ncu_launches_bench_n1.csv"))) if r and r[0].isdigit()]
+    assert len(rows) == 445
+    tot = collections.Counter()
+    for r in rows:
+        name = re.sub(r"\(.*$", "", r[4]).replace("void ", "").replace("tk::", "").strip()
+        tot[re.sub(r"<.*$", "", name)] += float(r[-1].replace(",", "")) / (1e6 if r[-2] in ("ns", "nsecond") else 1e3)
+    summary = open(os.path.join(ROOT, "profiles", "r01_ncu_launch_summary.txt")).read()
+    gram = float(re.search(r"^gram_row_kernel\S*\s+\S*\s+(\d+)\s+([\d.]+)", summary, re.M).group(2))
+    assert abs(gram - tot["gram_row_kernel"]) < 0.01
+    assert tot["gram_row_kernel"] > tot["lanczos_ttr_bulk_kernel"] > 0
