@@ -223,7 +223,6 @@ def run_reference(a):
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 def run_b200(a):
-    # keep stdout to the one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
     # Only the one JSON line may reach stdout (NCCL prints its version banner there): park fd 1 on stderr until
     # the line is ready.
     sys.stdout.flush()
