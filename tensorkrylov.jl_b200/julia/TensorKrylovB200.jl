@@ -1,8 +1,9 @@
 # TensorKrylovB200.jl -- the reference-side binding of libtensorkrylov_b200.so.
 #
 # Drop-in for `tensorkrylov!` (TensorKrylov.jl src/tensor_krylov_method.jl:36-125): same signature, same
-# ConvergenceData conventions, same three exits.  Load it after `using TensorKrylov`; it adds one method,
-# `tensorkrylov_b200!`, and (optionally) re-points `solve_tensorized_system` at it.
+# ConvergenceData conventions, same three exits.  Load it after `using TensorKrylov`; it adds `tensorkrylov_b200!`
+# and `solve_tensorized_system_b200`, and `TensorKrylovB200.install!()` re-points the package's own
+# `tensorkrylov!` (hence `solve_tensorized_system` and every driver) at the library for Float64 data.
 #
 # This file cannot be executed in the build image (no Julia there); every symbol it binds is exercised through
 # ctypes by the test-suite (tests/test_host_cpu.py::test_cabi_exports_every_declared_symbol and the -m gpu tests).
@@ -37,12 +38,15 @@ function set_operator!(h::Ptr{Cvoid}, s::Int, A::SparseMatrixCSC{Float64, Int64}
                 (Ptr{Cvoid}, Int32, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
                 h, s - 1, size(A, 1), A.colptr, A.rowval, A.nzval))
 end
-set_operator!(h, s, A::Symmetric{Float64, Matrix{Float64}}) =
+set_operator!(h::Ptr{Cvoid}, s::Int, A::Matrix{Float64}, uplo::Char = 'F') =
     check(ccall((:tk_set_operator_dense, libtk), Cint, (Ptr{Cvoid}, Int32, Int64, Ptr{Float64}, Cchar),
-                h, s - 1, size(A, 1), parent(A), A.uplo == 'L' ? 'L' : 'F'))
-set_operator!(h, s, A::Matrix{Float64}) =
-    check(ccall((:tk_set_operator_dense, libtk), Cint, (Ptr{Cvoid}, Int32, Int64, Ptr{Float64}, Cchar),
-                h, s - 1, size(A, 1), A, 'F'))
+                h, s - 1, size(A, 1), A, Cchar(uplo)))     # Cchar(...): ccall does not convert a Char by itself
+# Symmetric(R'R, :L) (tensor_struct.jl:77): the library reads the lower triangle of the parent, like the wrapper does
+set_operator!(h::Ptr{Cvoid}, s::Int, A::Symmetric{Float64, Matrix{Float64}}) =
+    A.uplo == 'L' ? set_operator!(h, s, parent(A), 'L') : set_operator!(h, s, Matrix(A), 'F')
+# anything else the gallery or a caller can produce (SymTridiagonal, Diagonal, other index types, views)
+set_operator!(h::Ptr{Cvoid}, s::Int, A::AbstractSparseMatrix) = set_operator!(h, s, SparseMatrixCSC{Float64, Int64}(A))
+set_operator!(h::Ptr{Cvoid}, s::Int, A::AbstractMatrix)       = set_operator!(h, s, Matrix{Float64}(A), 'F')
 
 """
     tensorkrylov_b200!(convergence_data, A, b, tol, nmax, orthonormalization_type; device = 0, flags = REFERENCE_H1)
@@ -77,7 +81,8 @@ function tensorkrylov_b200!(convergence_data::ConvergenceData{T}, A::KronMat{mat
         end
         end
         for s in 1:d
-            check(ccall((:tk_set_rhs, libtk), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64), h, s - 1, b[s], length(b[s])))
+            bs = convert(Vector{Float64}, b[s])   # KronProd{T} = Vector{<:AbstractVector{T}}: views are allowed
+            check(ccall((:tk_set_rhs, libtk), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64), h, s - 1, bs, length(bs)))
         end
         # exp-sum schedule: exactly the reference's two update_data! calls, hoisted out of the loop
         # (they depend on A_1, d, tol and k only -- tensor_krylov_method.jl:72-73)
@@ -125,6 +130,24 @@ function solve_tensorized_system_b200(system, nmax::Int, orth::Type{<:TensorDeco
     convergencedata = ConvergenceData{typeof(tol)}(nmax)
     tensorkrylov_b200!(convergencedata, system.A, system.b, tol, nmax, orth; kw...)
     return convergencedata
+end
+
+"""
+    TensorKrylovB200.install!()
+
+Make the GPU library THE solve path of the reference package: adds a method of `TensorKrylov.tensorkrylov!` for
+`Float64` data.  It is more specific than the package's generic method (tensor_krylov_method.jl:36-43), so
+`solve_tensorized_system`, the experiment drivers and the test-suite reach the library without any edit, while
+other element types keep falling through to the Julia implementation.
+"""
+function install!()
+    @eval TensorKrylov function tensorkrylov!(
+            convergence_data::ConvergenceData{Float64}, A::KronMat{matT, U}, b::KronProd{Float64}, tol::Float64,
+            nmax::Int, orthonormalization_type::Type{<:TensorDecomposition},
+            mode::Type{<:Mode} = SilentMode) where {matT, U<:Instance}
+        return $(tensorkrylov_b200!)(convergence_data, A, b, tol, nmax, orthonormalization_type)
+    end
+    return nothing
 end
 
 export tensorkrylov_b200!, solve_tensorized_system_b200
