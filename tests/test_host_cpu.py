@@ -231,3 +231,56 @@ def test_committed_ncu_launch_list_matches_its_summary():
     gram = float(re.search(r"^gram_row_kernel\S*\s+\S*\s+(\d+)\s+([\d.]+)", summary, re.M).group(2))
     assert abs(gram - tot["gram_row_kernel"]) < 0.01
     assert tot["gram_row_kernel"] > tot["lanczos_ttr_bulk_kernel"] > 0
+
+
+def test_argument_validation_needs_no_gpu(tk):
+    """Error behaviour of the boundary: shape and enum checks (the reference's @asserts, system.jl:27-28, and its
+    MethodErrors for unknown type tags) come back as TK_EINVAL / TK_EUNSUPPORTED with a message, before any CUDA
+    call; a null handle is an error, never a crash."""
+    import ctypes as C
+    lib, capi = tk._capi.lib, tk._capi
+
+    def create(d, ns, nmax, inst=0, cls=1, var=1, flags=1, dev=0, rank=0, world=1, uid=None):
+        h = C.c_void_p()
+        arr = (C.c_int64 * max(len(ns), 1))(*ns)
+        rc = lib.tk_create(C.byref(h), d, arr, nmax, inst, cls, var, flags, dev, rank, world, uid)
+        assert h.value is None or rc == 0
+        if rc == 0:
+            lib.tk_destroy(h)
+        return rc, lib.tk_last_error().decode()
+
+    EINVAL, EUNSUPPORTED = -1, -7
+    assert create(0, [10], 4)[0] == EINVAL
+    assert create(2, [10, 10], 0)[0] == EINVAL
+    rc, msg = create(2, [10, 12], 4)
+    assert rc == EUNSUPPORTED and "same order" in msg          # the reference itself only works for one n (DESIGN.md 7)
+    assert create(2, [10, 10], 11)[0] == EINVAL                  # nmax > n
+    assert create(2, [0, 0], 1)[0] == EINVAL
+    assert create(2, [10, 10], 4, inst=2)[0] == EINVAL
+    assert create(2, [10, 10], 4, cls=6)[0] == EINVAL
+    assert create(2, [10, 10], 4, var=3)[0] == EINVAL
+    assert create(2, [10, 10], 4, rank=1, world=1)[0] == EINVAL
+    assert create(2, [10, 10], 4, rank=0, world=2, uid=None)[0] == EINVAL
+    assert lib.tk_create(None, 2, (C.c_int64 * 2)(10, 10), 4, 0, 1, 1, 1, 0, 0, 1, None) == EINVAL
+    # null handle on every entry point that takes one
+    z = np.zeros(8)
+    i32, i64 = C.c_int32(), C.c_int64()
+    assert lib.tk_solve(None, 1e-8, C.byref(i32), C.byref(i64), C.byref(i32), capi.dptr(z), capi.dptr(z), capi.dptr(z)) == EINVAL
+    assert lib.tk_set_rhs(None, 0, capi.dptr(z), 8) == EINVAL
+    assert lib.tk_set_rhs_all(None, capi.dptr(z), 8) == EINVAL
+    assert lib.tk_set_schedule(None, 2, 1.0, 1, capi.dptr(z), capi.dptr(z)) == EINVAL
+    assert lib.tk_schedule_laplace(None, 1e-8) == EINVAL
+    assert lib.tk_local_modes(None, C.byref(i32), C.byref(i32)) == EINVAL
+    assert lib.tk_get_solution(None, 0, capi.dptr(z), capi.dptr(z), 0) == EINVAL
+    assert lib.tk_get_solution_all(None, capi.dptr(z), capi.dptr(z), 0) == EINVAL
+    assert lib.tk_launch_count(None, C.byref(i64)) == EINVAL
+    assert lib.tk_begin(None) == EINVAL
+    assert lib.tk_step_bases(None, 2) != 0 and lib.tk_compress(None, 2) != 0 and lib.tk_residual(None, 2, 0.0, None) != 0
+    lib.tk_destroy(None)                                          # no-op
+    # host-side helpers
+    assert lib.tk_nonsym_coefficients(1.0, 1e-9, 3, C.byref(i32), C.byref(i32), capi.dptr(z), capi.dptr(z)) == EINVAL  # cap too small
+    assert lib.tk_tables_load(b"/nonexistent/tables.bin") != 0
+    capi._tables_loaded = None                                    # a failed load must not leave a stale cache marker
+    capi.load_tables()
+    with pytest.raises(tk.TKError):
+        tk.sym_lookup(1e40, 1e-9)                                 # kappa outside the table (approximation.jl:71-76 loops forever)
