@@ -524,9 +524,7 @@ static int launch_ttr_t(tk_handle* h, int k, int threads, size_t smem) {
 
 template <int CPM, int ND, bool CONSTD, int RPT>
 static int launch_ttr_bulk_t(tk_handle* h, int k, int threads, size_t smem) {
-    // TK_TTR_ONEROUND=1: experimental one-reduction-round variant (tk_krylov.cuh), off unless asked for
-    auto kernel = env_int("TK_TTR_ONEROUND", 0) ? lanczos_ttr_bulk1_kernel<CPM, ND, CONSTD, RPT>
-                                                : lanczos_ttr_bulk_kernel<CPM, ND, CONSTD, RPT>;
+    auto kernel = lanczos_ttr_bulk_kernel<CPM, ND, CONSTD, RPT>;
     TK_TRY(allow_smem(kernel, smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(h->dk * CPM);

@@ -297,159 +297,6 @@ __global__ void __launch_bounds__(512) lanczos_ttr_bulk_kernel(KrylovParams p, i
 }
 
 // ------------------------------------------------------------------------------------------
-// EXPERIMENTAL (TK_TTR_ONEROUND=1, off by default): the bulk-copy 3-term step with ONE cluster-wide reduction round
-// instead of two.  With u = A v_k - beta_{k-1} v_{k-1} the five sums
-//     a1 = u.v_k   a2 = u.u   a3 = u.b   a4 = v_k.v_k   a5 = v_k.b
-// give alpha = a1, ||u - alpha v_k||^2 = a2 - alpha^2 (2 - a4) and (u - alpha v_k).b = a3 - alpha a5, so the pass that
-// writes v_{k+1} = (u - alpha v_k)/beta needs no second exchange.  The subtraction loses eps * a2/beta^2 (6 eps for
-// the 1D Laplacian); when beta^2 < 1e-4 a2 the kernel takes the exact second round of lanczos_ttr_bulk_kernel.  Every
-// CTA of a cluster forms the five sums from the same partials in the same order, so that decision is cluster-uniform.
-// ------------------------------------------------------------------------------------------
-template <int NV>   // NV sums at once; scratch: >= NV * 32 doubles
-__device__ __forceinline__ void block_sum_n(double (&v)[NV], double* scratch) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-#pragma unroll
-    for (int q = 0; q < NV; ++q) v[q] = warp_sum(v[q]);
-    __syncthreads();
-    if (lane == 0) {
-#pragma unroll
-        for (int q = 0; q < NV; ++q) scratch[q * 32 + w] = v[q];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < NV; ++q) v[q] = warp_sum((lane < nw) ? scratch[q * 32 + lane] : 0.0);
-}
-
-template <int CPM, int ND, bool CONSTD, int RPT>
-__global__ void __launch_bounds__(512) lanczos_ttr_bulk1_kernel(KrylovParams p, int k) {
-    const bool running = ttr_running(p, k);
-    extern __shared__ __align__(16) double smem[];
-    __shared__ double scratch[5 * 32];
-    __shared__ double slots5[5 * CPM];                        // round 1: five partials pushed by every rank
-    __shared__ double slots2[2 * CPM];                        // exact second round (rare)
-    __shared__ __align__(8) uint64_t bar;
-    const int s = blockIdx.x / CPM, part = blockIdx.x % CPM, n = p.n;
-    const int chunk = (((n + CPM - 1) / CPM) + 1) & ~1;
-    const int lo = part * chunk, hi = min(n, lo + chunk);
-    const double* vks = smem + TTR_HALO;
-    const double* us = smem + chunk + 2 * TTR_HALO;
-    const double* bs = us + chunk;
-    const OpDesc& op = p.ops[p.mode_op[s]];
-    double* Vs = p.V + (long long)s * p.vstride;
-    const double* vk = Vs + (long long)(k - 1) * p.ldv;
-    const double* vkm1 = (k >= 2) ? Vs + (long long)(k - 2) * p.ldv : nullptr;
-    const double* b = p.b + (long long)s * p.ldv;
-    double* vnew = Vs + (long long)k * p.ldv;
-    double* T = p.T + (long long)s * 3 * p.ncol;
-
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_addr(&bar)) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        const int he = (int)min((long long)((hi + 1) & ~1), p.ldv);
-        const int g0 = max(lo - TTR_HALO, 0), g1 = (int)min((long long)he + TTR_HALO, p.ldv);
-        const uint32_t bytes_v = (uint32_t)(g1 - g0) * 8u, bytes_s = (uint32_t)(he - lo) * 8u;
-        const uint32_t total = bytes_v + bytes_s * (vkm1 ? 2u : 1u);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(&bar)), "r"(total) : "memory");
-        bulk_load(smem + (g0 - lo + TTR_HALO), vk + g0, bytes_v, &bar);
-        if (vkm1) bulk_load(smem + chunk + 2 * TTR_HALO, vkm1 + lo, bytes_s, &bar);
-        bulk_load(smem + 2 * chunk + 2 * TTR_HALO, b + lo, bytes_s, &bar);
-    }
-    int offs[ND];
-    double cval[ND];
-#pragma unroll
-    for (int j = 0; j < ND; ++j) { offs[j] = op.offs[j]; cval[j] = CONSTD ? op.cval[j] : 0.0; }
-    const double beta_prev = (k >= 2) ? T[2 * p.ncol + (k - 2)] : 0.0;
-    __syncthreads();
-    mbar_wait(&bar, 0);
-    if (!running) return;
-
-    double u[RPT];
-    double a[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-        const int li = threadIdx.x + r * blockDim.x, i = lo + li;
-        double ui = 0.0;
-        if (i < hi) {
-#pragma unroll
-            for (int j = 0; j < ND; ++j) {
-                const int c = i + offs[j];
-                if ((unsigned)c < (unsigned)n)
-                    ui = fma(CONSTD ? cval[j] : __ldg(op.diag + (long long)j * op.ld + i), vks[li + offs[j]], ui);
-            }
-            if (vkm1) ui -= beta_prev * us[li];
-            const double vi = vks[li], bi = bs[li];
-            a[0] = fma(ui, vi, a[0]);
-            a[1] = fma(ui, ui, a[1]);
-            a[2] = fma(ui, bi, a[2]);
-            a[3] = fma(vi, vi, a[3]);
-            a[4] = fma(vi, bi, a[4]);
-        }
-        u[r] = ui;
-    }
-    block_sum_n<5>(a, scratch);
-    if (CPM > 1) {
-        cg::cluster_group cl = cg::this_cluster();
-        if (threadIdx.x < CPM) {
-            double* dst = cl.map_shared_rank(slots5, threadIdx.x) + 5 * part;
-#pragma unroll
-            for (int q = 0; q < 5; ++q) dst[q] = a[q];
-        }
-        cl.sync();
-#pragma unroll
-        for (int q = 0; q < 5; ++q) a[q] = 0.0;
-#pragma unroll
-        for (int r = 0; r < CPM; ++r) {
-#pragma unroll
-            for (int q = 0; q < 5; ++q) a[q] += slots5[5 * r + q];
-        }
-    }
-    const double alpha = a[0];
-    double beta2 = a[1] - alpha * alpha * (2.0 - a[3]);
-    double vb = a[2] - alpha * a[4];
-    const bool exact = !(beta2 > 1e-4 * a[1]);               // also taken for NaN / zero
-#pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-        const int li = threadIdx.x + r * blockDim.x;
-        if (lo + li < hi) u[r] -= alpha * vks[li];
-    }
-    if (exact) {
-        double acc = 0.0, accb = 0.0;
-#pragma unroll
-        for (int r = 0; r < RPT; ++r) {
-            const int li = threadIdx.x + r * blockDim.x;
-            if (lo + li < hi) { acc = fma(u[r], u[r], acc); accb = fma(u[r], bs[li], accb); }
-        }
-        block_sum2(acc, accb, scratch);
-        beta2 = acc; vb = accb;
-        if (CPM > 1) {
-            cg::cluster_group cl = cg::this_cluster();
-            if (threadIdx.x < CPM) {
-                double* dst = cl.map_shared_rank(slots2, threadIdx.x) + 2 * part;
-                dst[0] = acc; dst[1] = accb;
-            }
-            cl.sync();
-            beta2 = 0.0; vb = 0.0;
-#pragma unroll
-            for (int r = 0; r < CPM; ++r) { beta2 += slots2[2 * r]; vb += slots2[2 * r + 1]; }
-        }
-    }
-    const double beta = sqrt(beta2);
-    const double inv = (beta == 0.0) ? 0.0 : 1.0 / beta;
-#pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-        const int li = threadIdx.x + r * blockDim.x;
-        if (lo + li < hi) vnew[lo + li] = inv * u[r];
-    }
-    if (part == 0 && threadIdx.x == 0) {
-        T[k - 1] = alpha;
-        T[p.ncol + (k - 1)] = beta;
-        T[2 * p.ncol + (k - 1)] = beta;
-        p.bt[(long long)s * p.ncol + k] = inv * vb;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // CTA-wide modified Gram-Schmidt step k (orthogonal_bases.jl:15-37) for mode s.
 // v: working vector of n doubles (shared or global scratch); every thread owns the rows
 // i = tid, tid + blockDim, ... so the dot/axpy sequence needs no barrier besides the reduction.
