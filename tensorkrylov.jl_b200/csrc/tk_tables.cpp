@@ -129,7 +129,7 @@ static int load_dir(const std::string& dir) {
 int tables_sym_lookup(double kappa, double tol, int* t_out, int* digit_out, int* order_out, const double** omega,
                       const double** alpha) {
     if (!g_tables.loaded) return set_error(TK_ETABLE, "exponential-sum tables not loaded (tk_tables_load)");
-    if (!(kappa >= 1.0)) return set_error(TK_EINVAL, "condition number %g < 1", kappa);
+    if (!(kappa >= 1.0) || !std::isfinite(kappa)) return set_error(TK_EINVAL, "condition number %g is not a finite value >= 1", kappa);
     // parse_condition, approximation.jl:109-116
     int order = (int)std::floor(std::log10(kappa));
     int digit = (int)std::floor(kappa / std::pow(10.0, (double)order));

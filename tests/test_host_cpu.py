@@ -284,3 +284,7 @@ def test_argument_validation_needs_no_gpu(tk):
     capi.load_tables()
     with pytest.raises(tk.TKError):
         tk.sym_lookup(1e40, 1e-9)                                 # kappa outside the table (approximation.jl:71-76 loops forever)
+    for bad in (float("inf"), float("nan"), 0.5, -3.0):
+        with pytest.raises(tk.TKError) as ei:
+            tk.sym_lookup(bad, 1e-9)
+        assert ei.value.code == EINVAL
