@@ -288,3 +288,15 @@ def test_argument_validation_needs_no_gpu(tk):
         with pytest.raises(tk.TKError) as ei:
             tk.sym_lookup(bad, 1e-9)
         assert ei.value.code == EINVAL
+
+
+def test_device_code_is_the_measured_device_code(tk):
+    """profiles/sass_fingerprint.txt holds one md5 per kernel (SASS instruction text) of the library the numbers under
+    profiles/ were measured with.  A host-side change must leave all of them untouched; after an intended kernel
+    change re-measure and refresh the record with `python tools/sass_fingerprint.py --write`."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_fingerprint as sf
+    fp = sf.fingerprint(tk.LIB_PATH)
+    rec = dict(reversed(l.split("  ", 1)) for l in open(sf.REC).read().splitlines() if l.strip())
+    changed = sorted(k for k in set(fp) | set(rec) if fp.get(k) != rec.get(k))
+    assert not changed, f"device code differs from profiles/sass_fingerprint.txt for {len(changed)} kernels, e.g. {changed[:3]}"
