@@ -36,7 +36,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
-import make_golden as mg                      # noqa: E402
 import __graft_entry__ as entry               # noqa: E402
 
 REF = os.environ.get("TK_REFERENCE", "/root/reference")
@@ -44,38 +43,15 @@ DATA = os.path.join(REF, "experiments", "data")
 N = 200
 TOL = 1e-9                                    # every driver's default (reproduction.jl:10, parameterized_systems.jl:56)
 
-NAMES = [b"NonSymInstance", b"SymInstance", b"LaplaceDense", b"Laplace", b"ConvDiff", b"RandSPD", b"EigValMat",
-         b"TensorLanczosReorth", b"TensorLanczos", b"TensorArnoldi"]
-
-
 def decode(path):
-    """All 1-d arrays of one serialized Experiment, split per dimension."""
-    raw = open(path, "rb").read()
-    found = set(m.decode() for m in re.findall(b"(" + b"|".join(NAMES) + b")", raw))
-    arrs = mg.extract_arrays(path)
-    assert arrs[0][1] == "i"
-    dims = [int(x) for x in arrs[0][2]]
-    ints = [(o, a) for o, k, a in arrs if k == "i"][1:]
-    floats = [(o, a) for o, k, a in arrs if k == "f"]
-    first_hist = ints[0][0]
-    rhs_all = [a for o, a in floats if len(a) == N and o < first_hist]
-    assert len(rhs_all) == sum(dims), (path, len(rhs_all))
-    offs = np.concatenate([[0], np.cumsum(dims)])
+    """One serialized Experiment through the product's own decoder (tensorkrylov.jl_b200/experiments.py)."""
+    ex = entry.load_package().experiments.deserialize_from_file(path, N)
     runs = []
-    for i, d in enumerate(dims):
-        rhs = rhs_all[offs[i]:offs[i + 1]]
+    for d, rhs, c in zip(ex.dims, ex.rhs_vec, ex.conv_vector):
         assert all(np.array_equal(rhs[0], r) for r in rhs)      # system.jl:5-11: one vector, d times
-        o_it, iters = ints[i]
-        o_next = ints[i + 1][0] if i + 1 < len(ints) else len(raw)
-        hist = [a for o, a in floats if o_it < o < o_next and len(a) == len(iters)]
-        # current ConvergenceData: relres, projres, orth (convergence.jl:3-9); the four oldest files carry three
-        # spectral vectors in between (lambda_min, lambda_max, kappa)
-        assert len(hist) in (3, 6), (path, d, len(hist))
-        runs.append(dict(d=d, rhs=rhs[0], iterations=iters, relres=hist[0], projres=hist[1], orth=hist[-1]))
-    inst = "NonSymInstance" if "NonSymInstance" in found else "SymInstance"
-    cls = next(c for c in ("LaplaceDense", "ConvDiff", "RandSPD", "EigValMat", "Laplace") if c in found)
-    orth = next(c for c in ("TensorArnoldi", "TensorLanczosReorth", "TensorLanczos") if c in found)
-    return dict(instance=inst, cls=cls, orth=orth, runs=runs)
+        runs.append(dict(d=d, rhs=rhs[0], iterations=c.iterations, relres=c.relative_residual_norm,
+                         projres=c.projected_residual_norm, orth=c.orthogonality_data))
+    return dict(instance=ex.instance.__name__, cls=ex.matrixclass.__name__, orth=ex.orth_method.__name__, runs=runs)
 
 
 # ---- operators of the experiment drivers ----------------------------------------------------------------------

@@ -23,8 +23,6 @@ with eltype tag 0x0e = Float64, 0x08 = Int64, and <length> either
 field order, which is all this decoder relies on.
 """
 import os
-import re
-import struct
 import sys
 
 import numpy as np
@@ -34,28 +32,10 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "g
 
 
 def extract_arrays(path):
-    raw = open(path, "rb").read()
-    out = []
-    for m in re.finditer(rb"\x15\x00([\x0e\x08])", raw):
-        p = m.end()
-        et = m.group(1)
-        tag = raw[p]
-        if tag == 0x31:
-            n = struct.unpack("<i", raw[p + 1:p + 5])[0]
-            p += 5
-        elif tag in (0x06, 0x07):
-            n = raw[p + 1]
-            p += 2
-        elif 0xDF <= tag <= 0xFF:
-            n = tag - 0xDF
-            p += 1
-        else:
-            continue
-        if n < 0 or p + 8 * n > len(raw):
-            continue
-        dt = "<f8" if et == b"\x0e" else "<i8"
-        out.append((m.start(), "f" if et == b"\x0e" else "i", np.frombuffer(raw[p:p + 8 * n], dtype=dt).copy()))
-    return out
+    """The product's own decoder of the stream (tensorkrylov.jl_b200/experiments.py::julia_arrays)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    import __graft_entry__ as entry
+    return entry.load_package().experiments.julia_arrays(open(path, "rb").read())
 
 
 def decode_experiment(path, n):
