@@ -79,3 +79,32 @@ def test_decoder_reads_every_stored_file(tk):
                     assert np.array_equal(c.projected_residual_norm, z[f"{key}__projres_d{d}"])
                     assert np.array_equal(c.orthogonality_data, z[f"{key}__orth_d{d}"])
     assert seen == 30
+
+
+def test_driver_plumbing_with_an_oracle_backed_solver(tk, orc, tables, monkeypatch):
+    """The checks of the GPU driver test (tests/test_zz_gpu_corpus.py), with `solve_tensorized_system` -- the one call
+    that needs the GPU, and which the GPU suite tests on its own -- replaced by the CPU oracle: exercises everything the
+    drivers do around it (operators, class tags, right-hand sides, keyword plumbing, ConvergenceData bookkeeping)."""
+    cls_of = {tk.Laplace: orc.LAPLACE, tk.ConvDiff: orc.CONVDIFF, tk.RandSPD: orc.RANDSPD, tk.EigValMat: orc.EIGVALMAT}
+    var_of = {tk.TensorLanczos: orc.LANCZOS, tk.TensorLanczosReorth: orc.LANCZOS_REORTH, tk.TensorArnoldi: orc.ARNOLDI}
+    calls = []
+
+    def stand_in(system, nmax, orth, tol=1e-9, verbose=True, **kw):
+        assert not kw and verbose is False
+        inst = orc.NONSYM if system.instance is tk.NonSymInstance else orc.SYM
+        cls = cls_of[system.A.matrixclass]
+        A = [sp.csr_matrix(M) if sp.issparse(M) else np.asarray(M) for M in system.A.M]
+        assert all(abs(np.linalg.norm(b) - 1.0) < 1e-15 for b in system.b)          # TensorizedSystem normalised them
+        S = orc.tensorkrylov(A, system.b, tol, nmax, var_of[orth], inst, cls, tables if inst == orc.SYM else None,
+                             fast_solve=(cls != orc.EIGVALMAT and inst == orc.SYM))
+        cd = tk.ConvergenceData(nmax)
+        cd.status, cd.niterations = S.status, S.niterations
+        cd.relative_residual_norm[:len(S.relres)] = S.relres
+        calls.append((system.d, system.A.matrixclass.__name__, orth.__name__))
+        return cd
+
+    monkeypatch.setattr(tk.experiments, "solve_tensorized_system", stand_in)
+    C.check_experiment_drivers(tk, tol=1e-11)
+    assert len(calls) == 2 * (4 + 4 + 4) + 2 and {c[0] for c in calls} == {5, 10}
+    assert {c[1:] for c in calls} == {("Laplace", "TensorLanczosReorth"), ("ConvDiff", "TensorArnoldi"),
+                                      ("RandSPD", "TensorLanczosReorth"), ("EigValMat", "TensorLanczosReorth")}
