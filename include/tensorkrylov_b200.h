@@ -134,12 +134,21 @@ int tk_solve(tk_handle* h, double tol, int32_t* status, int64_t* niter, int32_t*
              double* relres, double* projres, double* orth);
 
 /* the KruskalTensor x returned on convergence (basis_tensor_mul!, utils.jl:478-488):
- * lambda[t], fmat = V_s[:,1:k] * Y_s, n x t column-major.  Valid after TK_CONVERGED,
- * or after any exit when force != 0 (uses the last iteration's y). */
+ * lambda[t], fmat = V_s[:,1:k] * Y_s, n x t column-major, of the iteration the loop left at.  Valid after
+ * TK_CONVERGED, or after any exit when force != 0 (the iterate of the last iteration).  tk_solution_rank gives t;
+ * every getter takes the capacity of the caller's buffers (in elements) and refuses buffers that are too small. */
 int tk_solution_rank(tk_handle* h, int32_t* t);
-int tk_get_solution(tk_handle* h, int32_t s, double* lambda, double* fmat, int32_t force);
-/* all local modes at once: fmat = [count][n*t], mode-major, each block n x t column-major (one D2H copy) */
-int tk_get_solution_all(tk_handle* h, double* lambda, double* fmat, int32_t force);
+int tk_get_solution(tk_handle* h, int32_t s, double* lambda, int32_t lambda_cap, double* fmat, int64_t fmat_cap,
+                    int32_t force);
+/* all local modes at once: fmat = [count][n*t], mode-major, each block n x t column-major.  One launch computes a
+ * chunk of modes while the previous chunk crosses PCIe; a destination from tk_alloc_host is written by DMA directly. */
+int tk_get_solution_all(tk_handle* h, double* lambda, int32_t lambda_cap, double* fmat, int64_t fmat_cap, int32_t force);
+/* the same into DEVICE memory of the handle's GPU (for callers that keep x on the device): one launch, no copy */
+int tk_get_solution_device(tk_handle* h, double* lambda, int32_t lambda_cap, double* fmat_dev, int64_t fmat_cap,
+                           int32_t force);
+/* page-locked host memory for results (and inputs) that should cross PCIe without a staging copy */
+int tk_alloc_host(void** out, int64_t bytes);
+int tk_free_host(void* p);
 
 /* ---- test-only single-phase entry points and state readers (parity/debug) */
 int tk_begin(tk_handle* h);                 /* orthonormalize!(decomp, b) + initialize_compressed_rhs: k = 1 */
@@ -159,6 +168,11 @@ int tk_get_orth_state(tk_handle* h, int32_t s, double* S /* running ||V'V - I||_
 int tk_tridiag_eig_batched(int32_t device, int32_t nb, int32_t k, const double* diag, const double* sub,
                            double* theta, double* Q, int32_t* fallbacks /* problems redone by the QL fallback, may be NULL */);
 
+/* Enqueueing.  tk_solve cuts the loop into segments of consecutive iterations; the device status word ends the
+ * solve (every later kernel returns at once), the host only stops enqueueing, two segments behind.  The second
+ * tk_solve of a handle with an unchanged configuration records each segment as a CUDA graph and replays it from
+ * then on (environment TK_GRAPH = 0 never, 2 from the first solve).  TK_FLAG_TIME_* solves use stream launches. */
+
 /* which: 0 = 3-term Lanczos step, 1 = orthogonality-monitor Gram row, 2 = Arnoldi/MGS step,
  * 3 = eigensolver, 4 = CP assembly + Gram, 5 = cross-mode combine, 6 = the whole last tk_solve
  * (CUDA events on the handle's stream, first enqueue to last kernel), 7 = from the last tk_timing_mark to the end of
@@ -167,6 +181,13 @@ int tk_tridiag_eig_batched(int32_t device, int32_t nb, int32_t k, const double* 
 int tk_timing_mark(tk_handle* h);
 int tk_get_timing(tk_handle* h, int32_t which, double* ms_total, int64_t* launches, double* algorithmic_bytes);
 int tk_launch_count(tk_handle* h, int64_t* launches);
+/* rows k0..k1 of the per-iteration record of the last solve, 8 doubles per iteration:
+ * {||Hy||^2, <Hy,b>, ||b~||^2, boundary term, r_comp, r_norm, t, lambda_min} (the terms of utils.jl:393, 441) */
+int tk_get_detail(tk_handle* h, int32_t k0, int32_t k1, double* out);
+/* how the last tk_solve was enqueued: CUDA graph launches (0 = direct stream launches), host time spent recording
+ * graphs, whether the cross-GPU exchange went through peer-mapped memory (1) or NCCL (0), number of segments */
+int tk_get_solve_info(tk_handle* h, int32_t* graphs_launched, double* graph_build_ms, int32_t* peer_exchange,
+                      int32_t* segments);
 
 #ifdef __cplusplus
 }

@@ -29,6 +29,7 @@ EXPORTS = [
     "tk_comm_unique_id", "tk_create", "tk_destroy", "tk_release_cache", "tk_local_modes", "tk_needs_mode",
     "tk_set_operator_csc", "tk_set_operator_dense", "tk_share_operator", "tk_share_operator_all", "tk_set_rhs", "tk_set_rhs_all",
     "tk_set_schedule", "tk_schedule_laplace", "tk_solve", "tk_solution_rank", "tk_get_solution", "tk_get_solution_all",
+    "tk_get_solution_device", "tk_alloc_host", "tk_free_host", "tk_get_detail", "tk_get_solve_info",
     "tk_begin", "tk_step_bases", "tk_compress", "tk_residual",
     "tk_get_H", "tk_get_V", "tk_get_bt", "tk_get_Y", "tk_get_eig", "tk_get_orth_state",
     "tk_tridiag_eig_batched", "tk_timing_mark", "tk_get_timing", "tk_launch_count",
@@ -74,8 +75,13 @@ def _load():
         "tk_schedule_laplace": (C.c_int, [p, f64]),
         "tk_solve": (C.c_int, [p, f64, pi32, pi64, pi32, pd, pd, pd]),
         "tk_solution_rank": (C.c_int, [p, pi32]),
-        "tk_get_solution": (C.c_int, [p, i32, pd, pd, i32]),
-        "tk_get_solution_all": (C.c_int, [p, pd, pd, i32]),
+        "tk_get_solution": (C.c_int, [p, i32, pd, i32, pd, i64, i32]),
+        "tk_get_solution_all": (C.c_int, [p, pd, i32, pd, i64, i32]),
+        "tk_get_solution_device": (C.c_int, [p, pd, i32, p, i64, i32]),
+        "tk_alloc_host": (C.c_int, [C.POINTER(p), i64]),
+        "tk_free_host": (C.c_int, [p]),
+        "tk_get_detail": (C.c_int, [p, i32, i32, pd]),
+        "tk_get_solve_info": (C.c_int, [p, pi32, pd, pi32, pi32]),
         "tk_begin": (C.c_int, [p]),
         "tk_step_bases": (C.c_int, [p, i32]),
         "tk_compress": (C.c_int, [p, i32]),
@@ -125,6 +131,32 @@ def load_tables(path=None):
     if _tables_loaded != path:
         check(lib.tk_tables_load(path.encode()))
         _tables_loaded = path
+
+
+class PinnedArray:
+    """A float64 numpy array over page-locked host memory from tk_alloc_host (results then cross PCIe by DMA,
+    without the staging copy a pageable destination needs).  The memory is returned by close() or with the object."""
+
+    def __init__(self, shape):
+        self.shape = tuple(int(x) for x in shape)
+        self.nbytes = 8 * int(np.prod(self.shape)) if self.shape else 8
+        ptr = C.c_void_p()
+        check(lib.tk_alloc_host(C.byref(ptr), self.nbytes))
+        self.ptr = ptr
+        buf = (C.c_double * max(self.nbytes // 8, 1)).from_address(ptr.value)
+        self.array = np.frombuffer(buf, dtype=np.float64, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            lib.tk_free_host(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def device_count():

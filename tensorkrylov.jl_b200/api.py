@@ -287,14 +287,53 @@ class Solver:
         check(lib.tk_solve(self.h, tol, C.byref(st), C.byref(nit), C.byref(tk), dptr(rr), dptr(pr), dptr(ol)))
         return dict(status=st.value, niterations=nit.value, term_k=tk.value, relres=rr, projres=pr, orth=ol)
 
-    def solution(self, force=False):
+    def solution_rank(self):
         t = C.c_int32()
         check(lib.tk_solution_rank(self.h, C.byref(t)))
-        lam = np.zeros(t.value)
-        buf = np.empty((max(self.count, 1), t.value, self.n))      # [mode][column][row] = n x t column-major per mode
-        check(lib.tk_get_solution_all(self.h, dptr(lam), dptr(buf), 1 if force else 0))
+        return t.value
+
+    def solution(self, force=False, pinned=False):
+        """x of the iteration the loop left at (basis_tensor_mul!, utils.jl:478-488): (lambda, {mode: n x t matrix}).
+        pinned=True puts the factor matrices into page-locked memory (DMA without a staging copy); the returned
+        matrices are then views of one PinnedArray kept alive in `self.pinned_result`."""
+        t = self.solution_rank()
+        lam = np.zeros(max(t, 1))
+        shape = (max(self.count, 1), t, self.n)      # [mode][column][row] = n x t column-major per mode
+        if pinned:
+            self.pinned_result = _capi.PinnedArray(shape)
+            buf = self.pinned_result.array
+        else:
+            buf = np.empty(shape)
+        check(lib.tk_get_solution_all(self.h, dptr(lam), len(lam), dptr(buf), buf.size, 1 if force else 0))
         fmat = {self.first + i: buf[i].T for i in range(self.count)}
-        return lam, fmat
+        return lam[:t], fmat
+
+    def solution_mode(self, s, force=False):
+        t = self.solution_rank()
+        lam = np.zeros(max(t, 1))
+        F = np.empty((t, self.n))
+        check(lib.tk_get_solution(self.h, s, dptr(lam), len(lam), dptr(F), F.size, 1 if force else 0))
+        return lam[:t], F.T
+
+    def solution_device(self, dev_ptr, capacity, force=False):
+        """Factor matrices into caller-owned DEVICE memory ([mode][t][n] doubles at dev_ptr); returns lambda."""
+        t = self.solution_rank()
+        lam = np.zeros(max(t, 1))
+        check(lib.tk_get_solution_device(self.h, dptr(lam), len(lam), C.c_void_p(dev_ptr), capacity, 1 if force else 0))
+        return lam[:t]
+
+    def detail(self, k0=2, k1=None):
+        """Per-iteration terms of the residual estimate of the last solve, rows k0..k1."""
+        k1 = self.nmax if k1 is None else k1
+        out = np.zeros((k1 - k0 + 1, 8))
+        check(lib.tk_get_detail(self.h, k0, k1, dptr(out)))
+        names = ("hy2", "hyb", "bb", "boundary", "r_comp", "r_norm", "t", "lambda_min")
+        return {nm: out[:, i].copy() for i, nm in enumerate(names)}
+
+    def solve_info(self):
+        g, ms, px, sg = C.c_int32(), C.c_double(), C.c_int32(), C.c_int32()
+        check(lib.tk_get_solve_info(self.h, C.byref(g), C.byref(ms), C.byref(px), C.byref(sg)))
+        return dict(graphs_launched=g.value, graph_build_ms=ms.value, peer_exchange=bool(px.value), segments=sg.value)
 
     # test-only phases and readers
     def begin(self): check(lib.tk_begin(self.h))

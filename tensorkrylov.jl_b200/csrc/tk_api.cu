@@ -11,6 +11,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -210,8 +211,13 @@ using namespace tk;
 struct tk_resources {
     int device = 0;
     cudaStream_t s_main = nullptr, s_asm = nullptr, s_eig[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t step_ev[8], eig_ev[8], asm_ev[8], ring_ev[8], ev_solve[2], ev_region;
-    int* status_ring = nullptr;
+    cudaEvent_t step_ev[8], eig_ev[8], asm_ev[8], seg_ev[4], join_ev[5], ev_fork, ev_solve[2], ev_region;
+    SolveCtl* hctl = nullptr;           // pinned + mapped: tolerance/epoch in, exit status out
+    SolveCtl* hctl_dev = nullptr;       // the same block as the device sees it
+    cudaStream_t s_copy = nullptr;      // device -> host copies of the solution, overlapped with its computation
+    cudaEvent_t copy_ev[2], fill_ev[2];
+    double* stage[2] = {nullptr, nullptr};   // pinned staging buffers for results that go to pageable memory
+    size_t stage_bytes = 0;
     std::vector<cudaEvent_t> ev_pool;   // timing events, grown on demand
 };
 static std::vector<tk_resources*> g_res_free;
@@ -231,16 +237,23 @@ static int acquire_resources(int device, tk_resources** out) {
     TK_CUDA(cudaStreamCreateWithFlags(&r->s_main, cudaStreamNonBlocking));
     TK_CUDA(cudaStreamCreateWithFlags(&r->s_asm, cudaStreamNonBlocking));
     for (auto& st : r->s_eig) TK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    TK_CUDA(cudaStreamCreateWithFlags(&r->s_copy, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) {
         TK_CUDA(cudaEventCreateWithFlags(&r->step_ev[i], cudaEventDisableTiming));
         TK_CUDA(cudaEventCreateWithFlags(&r->eig_ev[i], cudaEventDisableTiming));
         TK_CUDA(cudaEventCreateWithFlags(&r->asm_ev[i], cudaEventDisableTiming));
-        TK_CUDA(cudaEventCreateWithFlags(&r->ring_ev[i], cudaEventDisableTiming));
     }
+    for (auto& e : r->seg_ev) TK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : r->join_ev) TK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : r->copy_ev) TK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : r->fill_ev) TK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    TK_CUDA(cudaEventCreateWithFlags(&r->ev_fork, cudaEventDisableTiming));
     TK_CUDA(cudaEventCreate(&r->ev_solve[0]));
     TK_CUDA(cudaEventCreate(&r->ev_solve[1]));
     TK_CUDA(cudaEventCreate(&r->ev_region));
-    TK_CUDA(cudaMallocHost(&r->status_ring, 8 * sizeof(int)));
+    TK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&r->hctl), sizeof(SolveCtl), cudaHostAllocMapped));
+    TK_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&r->hctl_dev), r->hctl, 0));
+    std::memset(r->hctl, 0, sizeof(SolveCtl));
     *out = r.release();
     return 0;
 }
@@ -248,6 +261,8 @@ static int acquire_resources(int device, tk_resources** out) {
 struct tk_handle {
     tk_resources* res = nullptr;
     ~tk_handle() {
+        for (auto& sg : segs) if (sg.exec) cudaGraphExecDestroy(sg.exec);
+        for (void* q : px_opened) cudaIpcCloseMemHandle(q);
         if (res) {                      // also on a failed tk_create
             res->ev_pool.swap(ev_pool);
             std::lock_guard<std::mutex> lock(g_mutex);
@@ -258,7 +273,7 @@ struct tk_handle {
     int dk = 0;          // modes the Krylov kernels advance: dl, plus a shadow copy of global mode 0 (slot dl) when the
                          // reference's H_1-for-all-modes rule is on and another rank owns mode 0
     int eig_slot = 0;    // local slot whose T feeds class 0 under TK_FLAG_REFERENCE_H1
-    int instance = 0, matrixclass = 0, variant = 0, flags = 0, device = 0, rank = 0, world = 1;
+    int instance = 0, matrixclass = 0, variant = 0, flags = 0, device = 0, rank = 0, world = 1, sm_count = 148;
     long long ldv = 0;
     int per_mode = 0, ncls = 1;
     bool use_expm = false;   // compressed solve through the dense exponential (NonSymInstance, and the EigValMat class)
@@ -269,9 +284,40 @@ struct tk_handle {
     // (one SM each) and overlap the Krylov steps and the assembly of earlier iterations
     static constexpr int NEIG = 4, NBUF = 8;
     cudaStream_t stream3[NEIG] = {nullptr, nullptr, nullptr, nullptr};
-    std::vector<cudaEvent_t> eig_ev, asm_ev;
-    std::vector<cudaEvent_t> step_ev;  // step k done on `stream` -> `stream2` may start iteration k
+    // Dependencies between the streams: one event per kind and iteration (ring of 8), valid inside the segment that
+    // recorded it -- segments fork from and join into `stream`, so anything older is already complete
+    struct EvSlot { cudaEvent_t ev = nullptr; int k = -1, seg = -1; };
+    EvSlot step_slot[8], eigdone_slot[8], asm_slot[8];
+    int cur_seg = -1;
     ncclComm_t comm = nullptr;
+
+    // The iteration loop is cut into segments of consecutive iterations; a segment is enqueued either directly or as
+    // one CUDA graph launch (recorded once per configuration).  steps k0..k1 advance the Krylov bases, chains c0..c1
+    // are the compressed solve + residual estimate of those iterations; the chains of the last few steps of a
+    // segment are deferred into the next one so the Krylov stream never waits for them at a boundary.
+    struct Segment {
+        int k0 = 2, k1 = 1, c0 = 2, c1 = 1;
+        bool first = false;
+        cudaGraphExec_t exec = nullptr;
+        unsigned long long epoch = 0;
+        long long launches = 0;
+    };
+    std::vector<Segment> segs;
+    unsigned long long cfg_epoch = 1;    // bumped when anything baked into recorded launches changes
+    unsigned long long last_solve_epoch = 0;
+    long long solve_count = 0;
+    SolveCtl* hctl = nullptr;            // pinned (host view)
+    SolveCtl* hctl_dev = nullptr;        // pinned (device view)
+    DevBuf<SolveCtl> ctl_d;
+    double graph_build_ms = 0.0;         // host time spent recording + instantiating graphs in the last tk_solve
+    int graphs_launched = 0;
+
+    // peer exchange of the merged partials (world > 1): receive buffer + flags of this rank, peers' mapped views
+    PeerExchange px;
+    bool px_ready = false;
+    DevBuf<double> px_recv;
+    DevBuf<unsigned long long> px_flags;
+    std::vector<void*> px_opened;
 
     // Krylov state
     DevBuf<double> V, b, T, Hd, bt, g, S, orthS, bnorm2, vscratch;
@@ -291,7 +337,7 @@ struct tk_handle {
     int tmax = 0;
 
     // compressed solve / residual
-    DevBuf<double> theta, Q, Y, Z, E, bbm, partials, gathered, bnorm_d, relres_d, projres_d, orth_d, detail_d;
+    DevBuf<double> theta, Q, Y, Z, E, bbm, partials, gathered, relres_d, projres_d, orth_d, detail_d;
     DevBuf<double> eig_scratch;         // second k x k plane per eigenproblem (bisection kernel), same ring as Q
     DevBuf<int> eig_need;               // per problem: 1 if the QL fallback must recompute it
     DevBuf<unsigned int> ticket_d;      // last-CTA-done counter of combine_chunk_kernel
@@ -307,10 +353,6 @@ struct tk_handle {
     int last_k = 0, last_t = 0, last_tld = 0;
     double last_lam_inv = 0.0;
     bool begun = false;
-
-    // status polling
-    int* status_ring = nullptr;  // pinned
-    std::vector<cudaEvent_t> ring_ev;
 
     // timing
     struct Timed { int kind; cudaEvent_t a, b; double bytes; };
@@ -418,6 +460,8 @@ static int upload_schedule(tk_handle* h) {
     return 0;
 }
 
+static int setup_peer_exchange(tk_handle* h);
+
 static int alloc_work(tk_handle* h) {
     if (h->work_ready) return 0;
     const int kmax = h->nmax, tmax = std::max(h->tmax, 1);
@@ -445,7 +489,10 @@ static int alloc_work(tk_handle* h) {
     TK_TRY(h->partials.alloc((size_t)h->nchunks * h->pstride_max));
     TK_TRY(h->ticket_d.alloc(1));
     TK_TRY(h->merged.alloc((size_t)h->pstride_max));
-    if (h->world > 1) TK_TRY(h->gathered.alloc((size_t)h->world * h->pstride_max));
+    if (h->world > 1) {
+        TK_TRY(h->gathered.alloc((size_t)h->world * h->pstride_max));
+        TK_TRY(setup_peer_exchange(h));
+    }
     if (h->use_expm) {
         h->ex_ld = (h->nmax + 3) & ~3;
         // exponentials of up to ring_depth iterations are in flight (they only depend on the Krylov step); with one
@@ -666,6 +713,29 @@ static int launch_gram(tk_handle* h, int ncols, int base, int nmodes, int monito
     const double bytes = 8.0 * (double)h->n * (double)ncols * nmodes;
     const int U = env_int("TK_GRAM_U", 4);
     TimedScope ts(h, TM_GRAM, bytes, h->stream);
+    if (w_smem && env_int("TK_GRAM_BALANCED", 1)) {
+        // one wave of resident CTAs, each streaming an equal share of the flat (mode, column) list
+        const size_t smem_b = ((size_t)GRAM_BATCH * GRAM_PSTRIDE + ((h->ncol + 1) & ~1) + (size_t)((h->n + 1) & ~1)) * 8;
+        int per_sm = (threads == 256 && 2 * (smem_b + 2048) <= 227 * 1024) ? 2 : 1;
+        if (env_int("TK_GRAM_PER_SM", 0)) per_sm = env_int("TK_GRAM_PER_SM", 0);
+        const long long total = (long long)ncols * nmodes;
+        const int grid = (int)std::min<long long>(total, (long long)h->sm_count * per_sm);
+#define TK_GRAMB_LAUNCH(UU, TT)                                                                                  \
+        do {                                                                                                     \
+            TK_TRY(allow_smem(gram_row_balanced_kernel<UU, TT>, smem_b));                                        \
+            gram_row_balanced_kernel<UU, TT><<<grid, TT, smem_b, h->stream>>>(h->kp(), ncols, nmodes, base, wpc, \
+                                                                              monitor, h->tickets.p);            \
+        } while (0)
+        if (threads == 512) {
+            if (U == 8) TK_GRAMB_LAUNCH(8, 512); else if (U == 2) TK_GRAMB_LAUNCH(2, 512); else TK_GRAMB_LAUNCH(4, 512);
+        } else {
+            if (U == 8) TK_GRAMB_LAUNCH(8, 256); else if (U == 2) TK_GRAMB_LAUNCH(2, 256); else TK_GRAMB_LAUNCH(4, 256);
+        }
+#undef TK_GRAMB_LAUNCH
+        h->launches++;
+        TK_CUDA(cudaGetLastError());
+        return 0;
+    }
 #define TK_GRAM_LAUNCH(UU, TT)                                                                                   \
     do {                                                                                                         \
         TK_TRY(allow_smem(gram_row_kernel<UU, TT>, smem));                                                       \
@@ -935,7 +1005,7 @@ static int enqueue_assemble(tk_handle* h, int k) {
 }
 
 // residualnorm! (utils.jl:402-443) + exits of the loop body (tensor_krylov_method.jl:85-118)
-static int enqueue_residual(tk_handle* h, int k, double tol) {
+static int enqueue_residual(tk_handle* h, int k) {
     CompressParams c = make_cp(h, k);
     if (h->dl > 0 && h->use_expm) {      // the symmetric path did this inside assemble_cp_kernel
         TimedScope ts(h, TM_ASM, 0.0, h->stream2);
@@ -944,97 +1014,276 @@ static int enqueue_residual(tk_handle* h, int k, double tol) {
         TK_CUDA(cudaGetLastError());
     }
     const long long pst = 5LL * c.t * c.t + 2LL * c.t + 8;
-    TimedScope ts(h, TM_COMBINE, 0.0, h->stream2);
-    combine_chunk_kernel<<<h->nchunks, 256, 0, h->stream2>>>(c, h->dl, h->chunk_modes, h->chunk_base, h->partials.p, pst,
-                                                            h->orthS.p, (h->first == 0 && h->dl > 0) ? 0 : -1, h->ticket_d.p,
-                                                            h->merged.p);
-    h->launches++;
-    TK_CUDA(cudaGetLastError());
-    const double* parts = h->merged.p;
-    int nparts = 1;
-    if (h->world > 1) {
-        TK_NCCL(g_nccl.AllGather(h->merged.p, h->gathered.p, (size_t)pst, ncclDouble, h->comm, h->stream2));
-        parts = h->gathered.p;
-        nparts = h->world;
-    }
     FinalizeParams f;
-    f.k = k; f.t = c.t; f.nmax = h->nmax; f.nparts = nparts;
+    f.k = k; f.t = c.t; f.nmax = h->nmax; f.nparts = 1;
     f.fixed_iterations = (h->flags & TK_FLAG_FIXED_ITERATIONS) ? 1 : 0;
-    f.pstride = pst; f.partials = parts; f.omega = c.omega;
-    f.lam_inv = c.lam_inv; f.lambda_min = h->sched[k].lambda_min; f.tol = tol;
-    f.bnorm = h->bnorm_d.p;
+    f.pstride = pst; f.partials = h->merged.p; f.omega = c.omega;
+    f.lam_inv = c.lam_inv; f.lambda_min = h->sched[k].lambda_min;
+    f.ctl = h->ctl_d.p; f.hctl = h->hctl_dev;
     f.relres = h->relres_d.p; f.projres = h->projres_d.p; f.orth = h->orth_d.p; f.detail = h->detail_d.p;
     f.status = h->status_d.p; f.niter = h->niter_d.p; f.term_k = h->term_k_d.p;
+    // one GPU, or several with the peer exchange: the last CTA of the combine kernel also does the final merge
+    const int fin_here = (h->world == 1 || h->px_ready) ? 1 : 0;
+    PeerExchange px = h->px;
+    if (!h->px_ready) px.world = 1;
+    {
+        TimedScope ts(h, TM_COMBINE, 0.0, h->stream2);
+        combine_chunk_kernel<<<h->nchunks, 256, 0, h->stream2>>>(c, h->dl, h->chunk_modes, h->chunk_base, h->partials.p, pst,
+                                                                h->orthS.p, (h->first == 0 && h->dl > 0) ? 0 : -1,
+                                                                h->bnorm2.p, h->ticket_d.p, h->merged.p, fin_here, f, px);
+        h->launches++;
+        TK_CUDA(cudaGetLastError());
+    }
+    if (fin_here) return 0;
+    // fallback without peer-mapped memory: NCCL all-gather of the merged partials, then the final merge
+    TK_NCCL(g_nccl.AllGather(h->merged.p, h->gathered.p, (size_t)pst, ncclDouble, h->comm, h->stream2));
+    f.partials = h->gathered.p;
+    f.nparts = h->world;
     finalize_kernel<<<1, 256, 0, h->stream2>>>(f);
     h->launches++;
     TK_CUDA(cudaGetLastError());
     return 0;
 }
 
-static int reset_state(tk_handle* h) {
-    TK_TRY(upload_ops(h));
-    for (int s = 0; s < h->dk; ++s)
-        if (!h->rhs_set[s]) return set_error(TK_ESTATE, "right-hand side of mode %d not set", s < h->dl ? h->first + s : 0);
-    const int run[4] = {ST_RUNNING, ST_RUNNING, ST_RUNNING, 0}, zero = 0;
-    const long long nit = h->nmax;
-    TK_CUDA(cudaMemcpyAsync(h->status_d.p, run, sizeof(run), cudaMemcpyHostToDevice, h->stream));
-    TK_CUDA(cudaMemcpyAsync(h->term_k_d.p, &zero, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    TK_CUDA(cudaMemcpyAsync(h->eigfail_d.p, &zero, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    TK_CUDA(cudaMemcpyAsync(h->niter_d.p, &nit, sizeof(long long), cudaMemcpyHostToDevice, h->stream));
-    std::vector<double> ones(h->nmax, 1.0);   // ConvergenceData(nmax): ones (convergence.jl:11-20)
-    TK_CUDA(cudaMemcpyAsync(h->relres_d.p, ones.data(), 8 * (size_t)h->nmax, cudaMemcpyHostToDevice, h->stream));
-    TK_CUDA(cudaMemcpyAsync(h->projres_d.p, ones.data(), 8 * (size_t)h->nmax, cudaMemcpyHostToDevice, h->stream));
-    TK_CUDA(cudaMemcpyAsync(h->orth_d.p, ones.data(), 8 * (size_t)h->nmax, cudaMemcpyHostToDevice, h->stream));
-    TK_CUDA(cudaMemsetAsync(h->T.p, 0, 8 * h->T.count, h->stream));
-    TK_CUDA(cudaMemsetAsync(h->bt.p, 0, 8 * h->bt.count, h->stream));
-    TK_CUDA(cudaMemsetAsync(h->detail_d.p, 0, 8 * h->detail_d.count, h->stream));
-    // last-CTA ticket counters: a solve that terminated early may have left kernels half-skipped (every kernel
-    // checks the status word on entry), so the counters are not guaranteed to be back at zero
-    TK_CUDA(cudaMemsetAsync(h->tickets.p, 0, sizeof(unsigned int) * h->tickets.count, h->stream));
-    if (h->ticket_d.p) TK_CUDA(cudaMemsetAsync(h->ticket_d.p, 0, sizeof(unsigned int), h->stream));
-    if (h->Hd.p) TK_CUDA(cudaMemsetAsync(h->Hd.p, 0, 8 * h->Hd.count, h->stream));
-    TK_CUDA(cudaStreamSynchronize(h->stream));
-    h->ev_used = 0;
-    h->timed.clear();
-    h->launches = 0;
-    for (int i = 0; i < TM_KINDS; ++i) { h->tm_ms[i] = 0; h->tm_bytes[i] = 0; h->tm_launches[i] = 0; }
+// Peer exchange (world > 1): every rank exports its receive buffer and its flag array through CUDA IPC, the
+// 2 x 64-byte handles travel once over the existing NCCL communicator, and every rank maps everybody else's.  All
+// ranks must agree on the path, so the outcome is voted on (a second all-gather); if any rank could not map a
+// peer the solve keeps NCCL's all-gather.  Collective: called by all ranks from the first tk_solve / tk_compress.
+static int setup_peer_exchange(tk_handle* h) {
+    for (void* q : h->px_opened) cudaIpcCloseMemHandle(q);
+    h->px_opened.clear();
+    h->px_ready = false;
+    if (h->world > PX_MAX || !env_int("TK_PEER", 1)) return 0;
+    const long long slot = (h->pstride_max + 1) & ~1LL;
+    TK_TRY(h->px_recv.alloc((size_t)2 * h->world * slot));
+    TK_TRY(h->px_flags.alloc((size_t)h->world));
+    struct Rec { cudaIpcMemHandle_t recv, flag; int ok; int pad[15]; };
+    static_assert(sizeof(Rec) % 8 == 0, "record is shipped as doubles");
+    Rec mine;
+    std::memset(&mine, 0, sizeof(mine));
+    mine.ok = cudaIpcGetMemHandle(&mine.recv, h->px_recv.p) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.flag, h->px_flags.p) == cudaSuccess;
+    cudaGetLastError();
+    DevBuf<double> ex;
+    const size_t rd = sizeof(Rec) / 8;
+    TK_TRY(ex.alloc(rd * (h->world + 1)));
+    std::vector<Rec> all(h->world);
+    auto gather = [&]() -> int {
+        TK_CUDA(cudaMemcpyAsync(ex.p + rd * h->world, &mine, sizeof(Rec), cudaMemcpyHostToDevice, h->stream));
+        TK_NCCL(g_nccl.AllGather(ex.p + rd * h->world, ex.p, rd, ncclDouble, h->comm, h->stream));
+        TK_CUDA(cudaMemcpyAsync(all.data(), ex.p, sizeof(Rec) * h->world, cudaMemcpyDeviceToHost, h->stream));
+        TK_CUDA(cudaStreamSynchronize(h->stream));
+        return 0;
+    };
+    TK_TRY(gather());
+    PeerExchange px;
+    std::memset(&px, 0, sizeof(px));
+    px.world = h->world; px.rank = h->rank; px.slot_stride = slot;
+    bool ok = true;
+    for (int r = 0; r < h->world; ++r) ok = ok && all[r].ok;
+    for (int r = 0; r < h->world && ok; ++r) {
+        if (r == h->rank) { px.recv[r] = h->px_recv.p; px.flag[r] = h->px_flags.p; continue; }
+        void *pr = nullptr, *pf = nullptr;
+        if (cudaIpcOpenMemHandle(&pr, all[r].recv, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+        h->px_opened.push_back(pr);
+        if (cudaIpcOpenMemHandle(&pf, all[r].flag, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+        h->px_opened.push_back(pf);
+        px.recv[r] = static_cast<double*>(pr);
+        px.flag[r] = static_cast<unsigned long long*>(pf);
+    }
+    cudaGetLastError();
+    mine.ok = ok ? 1 : 0;
+    TK_TRY(gather());                       // vote: also orders every rank's mapping before anybody's first store
+    for (int r = 0; r < h->world; ++r) ok = ok && all[r].ok;
+    if (!ok) {
+        for (void* q : h->px_opened) cudaIpcCloseMemHandle(q);
+        h->px_opened.clear();
+        cudaGetLastError();
+        if (env_int("TK_PEER", 1) == 2) return set_error(TK_ECUDA, "peer mapping of the exchange buffers failed (TK_PEER=2 forbids the NCCL fallback)");
+        return 0;
+    }
+    h->px = px;
+    h->px_ready = true;
     return 0;
 }
 
-// orthonormalize!(decomp, b), initialize_compressed_rhs, kronprodnorm   (tensor_krylov_method.jl:48-55)
-static int begin_solve(tk_handle* h) {
-    TK_TRY(reset_state(h));
+static int prepare(tk_handle* h, bool with_schedule) {
+    const bool od = h->ops_dirty, sd = h->sched_dirty, wr = h->work_ready;
+    TK_TRY(upload_ops(h));
+    for (int s = 0; s < h->dk; ++s)
+        if (!h->rhs_set[s]) return set_error(TK_ESTATE, "right-hand side of mode %d not set", s < h->dl ? h->first + s : 0);
+    if (with_schedule) {
+        TK_TRY(upload_schedule(h));
+        TK_TRY(alloc_work(h));
+    }
+    if (od || (with_schedule && (sd || !wr))) h->cfg_epoch++;
+    // working vector of the MGS step when it does not fit in shared memory
+    const size_t need_gram = ((size_t)32 * GRAM_PSTRIDE + ((h->ncol + 1) & ~1) + (size_t)h->n) * 8;
+    const size_t need_mgs = ((size_t)h->ncol + (size_t)h->n) * 8;
+    if ((need_gram > smem_limit(h) || need_mgs > smem_limit(h)) && !h->vscratch.p) {
+        TK_TRY(h->vscratch.alloc((size_t)h->dk * h->ldv));
+        h->cfg_epoch++;
+    }
+    return 0;
+}
+
+// Values the recorded launches read at run time instead of carrying them as arguments
+static void arm_solve(tk_handle* h, double tol) {
+    h->solve_count++;
+    h->hctl->tol = tol;
+    h->hctl->epoch = h->solve_count * (long long)(h->nmax + 2);
+    h->hctl->term_k = 0;
+    h->hctl->niter = h->nmax;
+    *reinterpret_cast<volatile int*>(&h->hctl->status) = ST_RUNNING;
+    for (int i = 0; i < 8; ++i) { h->step_slot[i].k = -1; h->eigdone_slot[i].k = -1; h->asm_slot[i].k = -1; }
+    h->ev_used = 0;
+    h->timed.clear();
+    h->launches = 0;
+    h->graph_build_ms = 0.0;
+    h->graphs_launched = 0;
+    for (int i = 0; i < TM_KINDS; ++i) { h->tm_ms[i] = 0; h->tm_bytes[i] = 0; h->tm_launches[i] = 0; }
+}
+
+// orthonormalize!(decomp, b), initialize_compressed_rhs, kronprodnorm   (tensor_krylov_method.jl:48-55).
+// No host round trip: kronprodnorm(b) = sqrt(prod_s b_s.b_s) travels with the cross-mode partials (bnorm2 -> combine).
+static int enqueue_begin(tk_handle* h) {
+    ResetParams r;
+    r.status4 = h->status_d.p; r.term_k = h->term_k_d.p; r.eigfail = h->eigfail_d.p; r.niter = h->niter_d.p;
+    r.relres = h->relres_d.p; r.projres = h->projres_d.p; r.orth = h->orth_d.p; r.nmax = h->nmax;
+    r.tickets = h->tickets.p; r.ntickets = (int)h->tickets.count; r.ticket1 = h->ticket_d.p;
+    r.ctl = h->ctl_d.p; r.hctl = h->hctl_dev;
+    reset_kernel<<<1, 256, 0, h->stream>>>(r);
+    h->launches++;
+    TK_CUDA(cudaGetLastError());
+    TK_CUDA(cudaMemsetAsync(h->T.p, 0, 8 * h->T.count, h->stream));
+    TK_CUDA(cudaMemsetAsync(h->bt.p, 0, 8 * h->bt.count, h->stream));
+    TK_CUDA(cudaMemsetAsync(h->detail_d.p, 0, 8 * h->detail_d.count, h->stream));
+    if (h->Hd.p) TK_CUDA(cudaMemsetAsync(h->Hd.p, 0, 8 * h->Hd.count, h->stream));
     if (h->dk > 0) {
         init_basis_kernel<<<h->dk, 512, 0, h->stream>>>(h->kp(), h->bnorm2.p);
         h->launches++;
         TK_CUDA(cudaGetLastError());
     }
-    // b_norm = sqrt(prod_s b_s.b_s) over ALL modes, in mode order
-    std::vector<double> bn2(std::max(h->dl, 1));
-    TK_CUDA(cudaMemcpyAsync(bn2.data(), h->bnorm2.p, 8 * (size_t)h->dl, cudaMemcpyDeviceToHost, h->stream));
-    TK_CUDA(cudaStreamSynchronize(h->stream));
-    double prod = 1.0;
-    for (int s = 0; s < h->dl; ++s) prod *= bn2[s];
-    if (h->world > 1) {
-        DevBuf<double> tmp;
-        TK_TRY(tmp.alloc(h->world + 1));
-        TK_CUDA(cudaMemcpyAsync(tmp.p + h->world, &prod, 8, cudaMemcpyHostToDevice, h->stream));
-        TK_NCCL(g_nccl.AllGather(tmp.p + h->world, tmp.p, 1, ncclDouble, h->comm, h->stream));
-        std::vector<double> all(h->world);
-        TK_CUDA(cudaMemcpyAsync(all.data(), tmp.p, 8 * (size_t)h->world, cudaMemcpyDeviceToHost, h->stream));
-        TK_CUDA(cudaStreamSynchronize(h->stream));
-        prod = 1.0;
-        for (int r = 0; r < h->world; ++r) prod *= all[r];
-    }
-    const double bnorm = std::sqrt(prod);
-    TK_CUDA(cudaMemcpyAsync(h->bnorm_d.p, &bnorm, 8, cudaMemcpyHostToDevice, h->stream));
-    TK_CUDA(cudaStreamSynchronize(h->stream));
     // Gram "row" of column 1 starts the orthogonality bookkeeping, then step k = 1
     const int mode0 = (h->first == 0 && h->dl > 0) ? 1 : 0;
     const int nmon = h->variant == TK_LANCZOS_REORTH ? h->dk : mode0;
     TK_TRY(launch_gram(h, 1, 0, nmon, 0));
     TK_TRY(enqueue_step_bases(h, 1));
+    return 0;
+}
+
+static int begin_solve(tk_handle* h, double tol) {
+    TK_TRY(prepare(h, false));
+    arm_solve(h, tol);
+    TK_TRY(enqueue_begin(h));
     h->begun = true;
+    return 0;
+}
+
+// ---- dependencies inside a segment -------------------------------------------------------
+static int slot_record(tk_handle* h, tk_handle::EvSlot* ring, int k, cudaStream_t st) {
+    tk_handle::EvSlot& sl = ring[k & 7];
+    TK_CUDA(cudaEventRecord(sl.ev, st));
+    sl.k = k; sl.seg = h->cur_seg;
+    return 0;
+}
+static int slot_wait(tk_handle* h, tk_handle::EvSlot* ring, int k, cudaStream_t st) {
+    const tk_handle::EvSlot& sl = ring[k & 7];
+    if (sl.k == k && sl.seg == h->cur_seg) TK_CUDA(cudaStreamWaitEvent(st, sl.ev, 0));
+    return 0;   // recorded in an earlier segment: complete before this one started
+}
+
+// eigensolve -> CP assembly -> residual estimate of iteration k on the side streams
+static int enqueue_chain(tk_handle* h, int k) {
+    cudaStream_t es = h->stream3[k % tk_handle::NEIG];
+    TK_TRY(slot_wait(h, h->step_slot, k, es));                             // needs the Krylov step k
+    if (k - h->ring_depth >= 2) TK_TRY(slot_wait(h, h->asm_slot, k - h->ring_depth, es));   // its ring buffer is free
+    TK_TRY(enqueue_eig(h, k));
+    TK_TRY(slot_record(h, h->eigdone_slot, k, es));
+    TK_TRY(slot_wait(h, h->eigdone_slot, k, h->stream2));
+    TK_TRY(enqueue_assemble(h, k));
+    TK_TRY(slot_record(h, h->asm_slot, k, h->stream2));
+    TK_TRY(enqueue_residual(h, k));
+    return 0;
+}
+
+static std::vector<cudaStream_t> side_streams(const tk_handle* h) {
+    std::vector<cudaStream_t> out;
+    auto add = [&](cudaStream_t st) {
+        if (st == h->stream) return;
+        for (auto q : out) if (q == st) return;
+        out.push_back(st);
+    };
+    add(h->stream2);
+    for (auto st : h->stream3) add(st);
+    return out;
+}
+
+static int enqueue_segment(tk_handle* h, int idx) {
+    const tk_handle::Segment& sg = h->segs[idx];
+    h->cur_seg = idx;
+    if (sg.first) TK_TRY(enqueue_begin(h));
+    const std::vector<cudaStream_t> side = side_streams(h);
+    TK_CUDA(cudaEventRecord(h->res->ev_fork, h->stream));
+    for (auto st : side) TK_CUDA(cudaStreamWaitEvent(st, h->res->ev_fork, 0));
+    for (int k = sg.c0; k <= sg.c1 && k < sg.k0; ++k) TK_TRY(enqueue_chain(h, k));      // deferred by the last segment
+    for (int k = sg.k0; k <= sg.k1; ++k) {
+        TK_TRY(enqueue_step_bases(h, k));
+        TK_TRY(slot_record(h, h->step_slot, k, h->stream));
+        if (k >= sg.c0 && k <= sg.c1) TK_TRY(enqueue_chain(h, k));
+    }
+    for (size_t i = 0; i < side.size(); ++i) {
+        TK_CUDA(cudaEventRecord(h->res->join_ev[i], side[i]));
+        TK_CUDA(cudaStreamWaitEvent(h->stream, h->res->join_ev[i], 0));
+    }
+    return 0;
+}
+
+static void plan_segments(tk_handle* h) {
+    if (!h->segs.empty()) return;
+    // short segments first (a solve that ends after a few iterations has little enqueued behind its exit), then 16
+    const int cap = std::max(1, env_int("TK_SEG", 16)), lag = std::max(0, env_int("TK_SEG_LAG", 3));
+    const bool fixed = (h->flags & TK_FLAG_FIXED_ITERATIONS) != 0;
+    int k = 2, size = fixed ? cap : std::min(cap, 4), count = 0, prev_c1 = 1;
+    do {
+        tk_handle::Segment sg;
+        sg.first = h->segs.empty();
+        sg.k0 = k;
+        sg.k1 = std::min(h->nmax, k + size - 1);
+        const bool last = sg.k1 >= h->nmax;
+        sg.c0 = prev_c1 + 1;
+        sg.c1 = last ? h->nmax : std::max(sg.c0 - 1, sg.k1 - lag);
+        prev_c1 = sg.c1;
+        h->segs.push_back(sg);
+        k = sg.k1 + 1;
+        if (++count >= 2 && size < cap) { size = std::min(cap, size * 2); count = 0; }
+    } while (k <= h->nmax);
+}
+
+static int launch_segment(tk_handle* h, int idx, bool graph) {
+    tk_handle::Segment& sg = h->segs[idx];
+    if (!graph) return enqueue_segment(h, idx);
+    if (!sg.exec || sg.epoch != h->cfg_epoch) {
+        const auto t0 = std::chrono::steady_clock::now();
+        if (sg.exec) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; }
+        const long long before = h->launches;
+        TK_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+        const int rc = enqueue_segment(h, idx);
+        cudaGraph_t g = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+        sg.launches = h->launches - before;
+        h->launches = before;
+        if (rc != 0) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return rc; }
+        if (e != cudaSuccess) { cudaGetLastError(); return set_error(TK_ECUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e)); }
+        const cudaError_t ei = cudaGraphInstantiate(&sg.exec, g, 0);
+        cudaGraphDestroy(g);
+        if (ei != cudaSuccess) { sg.exec = nullptr; return set_error(TK_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ei)); }
+        sg.epoch = h->cfg_epoch;
+        h->graph_build_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    TK_CUDA(cudaGraphLaunch(sg.exec, h->stream));
+    h->launches += sg.launches;
+    h->graphs_launched++;
     return 0;
 }
 
@@ -1117,6 +1366,7 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
     h->dk = h->dl + (shadow ? 1 : 0);
     h->eig_slot = shadow ? h->dl : 0;
 
+    TK_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
     TK_TRY(acquire_resources(device, &h->res));
     tk_resources* r = h->res;
     h->stream = r->s_main;
@@ -1126,13 +1376,12 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
         else if (i >= env_int("TK_EIG_STREAMS", tk_handle::NEIG)) h->stream3[i] = r->s_eig[0];
         else h->stream3[i] = r->s_eig[i];
     }
-    h->eig_ev.assign(r->eig_ev, r->eig_ev + 8);
-    h->asm_ev.assign(r->asm_ev, r->asm_ev + 8);
-    h->step_ev.assign(r->step_ev, r->step_ev + 8);
-    h->ring_ev.assign(r->ring_ev, r->ring_ev + 8);
+    for (int i = 0; i < 8; ++i) {
+        h->step_slot[i].ev = r->step_ev[i]; h->eigdone_slot[i].ev = r->eig_ev[i]; h->asm_slot[i].ev = r->asm_ev[i];
+    }
     h->ev_solve[0] = r->ev_solve[0]; h->ev_solve[1] = r->ev_solve[1];
     h->ev_region = r->ev_region;
-    h->status_ring = r->status_ring;
+    h->hctl = r->hctl; h->hctl_dev = r->hctl_dev;
     h->ev_pool.swap(r->ev_pool);
     const size_t dl = std::max(h->dk, 1);
     TK_TRY(h->V.alloc(dl * (size_t)h->ncol * h->ldv, false));
@@ -1151,7 +1400,7 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
     TK_TRY(h->term_k_d.alloc(1));
     TK_TRY(h->eigfail_d.alloc(1));
     TK_TRY(h->niter_d.alloc(1));
-    TK_TRY(h->bnorm_d.alloc(1));
+    TK_TRY(h->ctl_d.alloc(1));
     TK_TRY(h->relres_d.alloc(nmax));
     TK_TRY(h->projres_d.alloc(nmax));
     TK_TRY(h->orth_d.alloc(nmax));
@@ -1195,12 +1444,19 @@ int tk_release_cache(void) {
         cudaSetDevice(r->device);
         cudaStreamDestroy(r->s_main); cudaStreamDestroy(r->s_asm);
         for (auto st : r->s_eig) cudaStreamDestroy(st);
+        cudaStreamDestroy(r->s_copy);
         for (int i = 0; i < 8; ++i) {
-            cudaEventDestroy(r->step_ev[i]); cudaEventDestroy(r->eig_ev[i]); cudaEventDestroy(r->asm_ev[i]); cudaEventDestroy(r->ring_ev[i]);
+            cudaEventDestroy(r->step_ev[i]); cudaEventDestroy(r->eig_ev[i]); cudaEventDestroy(r->asm_ev[i]);
         }
+        for (auto e : r->seg_ev) cudaEventDestroy(e);
+        for (auto e : r->join_ev) cudaEventDestroy(e);
+        for (auto e : r->copy_ev) cudaEventDestroy(e);
+        for (auto e : r->fill_ev) cudaEventDestroy(e);
+        cudaEventDestroy(r->ev_fork);
         cudaEventDestroy(r->ev_solve[0]); cudaEventDestroy(r->ev_solve[1]); cudaEventDestroy(r->ev_region);
         for (auto e : r->ev_pool) cudaEventDestroy(e);
-        cudaFreeHost(r->status_ring);
+        cudaFreeHost(r->hctl);
+        for (auto q : r->stage) if (q) cudaFreeHost(q);
         delete r;
     }
     g_res_free.clear();
@@ -1446,7 +1702,7 @@ int tk_schedule_laplace(tk_handle* h, double tol) {
 int tk_begin(tk_handle* h) {
     if (!h) return set_error(TK_EINVAL, "null handle");
     TK_CUDA(cudaSetDevice(h->device));
-    TK_TRY(begin_solve(h));
+    TK_TRY(begin_solve(h, 0.0));
     TK_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -1464,8 +1720,7 @@ int tk_compress(tk_handle* h, int32_t k) {
     if (!h || !h->begun) return set_error(TK_ESTATE, "call tk_begin first");
     if (k < 2 || k > h->nmax) return set_error(TK_EINVAL, "k = %d outside 2..nmax", k);
     TK_CUDA(cudaSetDevice(h->device));
-    TK_TRY(upload_schedule(h));
-    TK_TRY(alloc_work(h));
+    TK_TRY(prepare(h, true));
     TK_TRY(enqueue_eig(h, k));
     TK_CUDA(cudaStreamSynchronize(h->stream3[k % tk_handle::NEIG]));
     TK_TRY(enqueue_assemble(h, k));
@@ -1476,7 +1731,8 @@ int tk_compress(tk_handle* h, int32_t k) {
 int tk_residual(tk_handle* h, int32_t k, double tol, double* out8) {
     if (!h || !h->begun || h->last_k != k) return set_error(TK_ESTATE, "call tk_compress(k) first");
     TK_CUDA(cudaSetDevice(h->device));
-    TK_TRY(enqueue_residual(h, k, tol));
+    TK_CUDA(cudaMemcpy(&h->ctl_d.p->tol, &tol, sizeof(double), cudaMemcpyHostToDevice));
+    TK_TRY(enqueue_residual(h, k));
     TK_CUDA(cudaStreamSynchronize(h->stream2));
     if (out8) TK_CUDA(cudaMemcpy(out8, h->detail_d.p + (size_t)k * 8, 64, cudaMemcpyDeviceToHost));
     return 0;
@@ -1486,49 +1742,36 @@ int tk_solve(tk_handle* h, double tol, int32_t* status, int64_t* niter, int32_t*
              double* orth) {
     if (!h) return set_error(TK_EINVAL, "null handle");
     TK_CUDA(cudaSetDevice(h->device));
-    TK_TRY(upload_schedule(h));
-    TK_TRY(alloc_work(h));
+    const unsigned long long epoch_before = h->cfg_epoch;
+    TK_TRY(prepare(h, true));
+    plan_segments(h);
+    // Enqueue mode.  Kernel timing needs events between the launches, so it takes the direct path.  Otherwise the
+    // segments are recorded as CUDA graphs the second time a handle solves with an unchanged configuration (a
+    // one-shot solve would pay for the recording without using it twice); TK_GRAPH = 0 never, 2 from the first solve.
+    const int gmode = env_int("TK_GRAPH", 1);
+    const bool timed = (h->flags & (TK_FLAG_TIME_KERNELS | TK_FLAG_TIME_ALL)) != 0;
+    const bool repeat = h->last_solve_epoch == h->cfg_epoch && epoch_before == h->cfg_epoch;
+    const bool graph = !timed && (gmode >= 2 || (gmode == 1 && repeat));
+    h->last_solve_epoch = h->cfg_epoch;
+    arm_solve(h, tol);
+    const bool fixed = (h->flags & TK_FLAG_FIXED_ITERATIONS) != 0;
     TK_CUDA(cudaEventRecord(h->ev_solve[0], h->stream));
-    TK_TRY(begin_solve(h));
-    // Two streams: `stream` advances the Krylov bases (iteration k+1 needs nothing from the compressed solve of
-    // iteration k), `stream2` runs eigensolve -> CP assembly -> residual for iteration k as soon as step k is
-    // done.  The host polls the device status word LAG iterations behind, so it never stalls the GPU queue.
-    const int RING = 8;
-    int st = ST_RUNNING;
-    for (int k = 2; k <= h->nmax; ++k) {
-        // how far the enqueue front runs ahead of the last status the host has seen: short while the iterations are
-        // cheap (an early exit then wastes little), longer once the assembly/residual chain has real latency
-        const int LAG = k <= 12 ? 3 : 6;
-        if (k - LAG >= 2) {
-            const int slot = (k - LAG) % RING;
-            TK_CUDA(cudaEventSynchronize(h->ring_ev[slot]));
-            if (h->status_ring[slot] != ST_RUNNING) break;
+    // The device decides: once finalize has set the status word every later kernel returns at once.  The host only
+    // stops enqueueing: it looks at the pinned copy of the status two segments behind the launch front, so the GPU
+    // queue never drains.
+    const int nseg = (int)h->segs.size();
+    for (int i = 0; i < nseg; ++i) {
+        if (!fixed && i >= 2) {
+            TK_CUDA(cudaEventSynchronize(h->res->seg_ev[(i - 2) & 3]));
+            if (*reinterpret_cast<volatile int*>(&h->hctl->status) != ST_RUNNING) break;
         }
-        TK_TRY(enqueue_step_bases(h, k));
-        const int slot = k % RING;
-        TK_CUDA(cudaEventRecord(h->step_ev[slot], h->stream));
-        // eigensolver stream: needs step k; its (theta, Q) buffer k&1 was last read by the assembly of k-2
-        cudaStream_t es = h->stream3[k % tk_handle::NEIG];
-        TK_CUDA(cudaStreamWaitEvent(es, h->step_ev[slot], 0));
-        if (k - h->ring_depth >= 2) TK_CUDA(cudaStreamWaitEvent(es, h->asm_ev[(k - h->ring_depth) % RING], 0));
-        TK_TRY(enqueue_eig(h, k));
-        TK_CUDA(cudaEventRecord(h->eig_ev[slot], es));
-        // assembly + residual stream
-        TK_CUDA(cudaStreamWaitEvent(h->stream2, h->eig_ev[slot], 0));
-        TK_TRY(enqueue_assemble(h, k));
-        TK_CUDA(cudaEventRecord(h->asm_ev[slot], h->stream2));
-        TK_TRY(enqueue_residual(h, k, tol));
-        TK_CUDA(cudaMemcpyAsync(&h->status_ring[slot], h->status_d.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream2));
-        TK_CUDA(cudaEventRecord(h->ring_ev[slot], h->stream2));
+        TK_TRY(launch_segment(h, i, graph));
+        TK_CUDA(cudaEventRecord(h->res->seg_ev[i & 3], h->stream));
     }
-    // join: the solve window ends when both streams have drained
-    TK_CUDA(cudaEventRecord(h->step_ev[0], h->stream2));
-    TK_CUDA(cudaStreamWaitEvent(h->stream, h->step_ev[0], 0));
     TK_CUDA(cudaEventRecord(h->ev_solve[1], h->stream));
-    TK_CUDA(cudaStreamSynchronize(h->stream));
-    TK_CUDA(cudaStreamSynchronize(h->stream2));
-    for (auto es : h->stream3) TK_CUDA(cudaStreamSynchronize(es));
-    int tk_ = 0, eigfail = 0;
+    TK_CUDA(cudaStreamSynchronize(h->stream));      // every segment joins its side streams into this one
+    h->begun = true;
+    int st = ST_RUNNING, tk_ = 0, eigfail = 0;
     long long nit = 0;
     TK_CUDA(cudaMemcpy(&st, h->status_d.p, sizeof(int), cudaMemcpyDeviceToHost));
     TK_CUDA(cudaMemcpy(&tk_, h->term_k_d.p, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1544,6 +1787,14 @@ int tk_solve(tk_handle* h, double tol, int32_t* status, int64_t* niter, int32_t*
         TK_CUDA(cudaEventElapsedTime(&ms, h->ev_solve[0], h->ev_solve[1]));
         h->tm_ms[TM_SOLVE] = ms; h->tm_launches[TM_SOLVE] = 1;
     }
+    // The compressed solution resident in Y is the one of the iteration the loop left at: the assembly kernels of
+    // the iterations enqueued behind it returned at once.
+    if (tk_ >= 2) {
+        const SchedEntry& se = h->sched[tk_];
+        h->last_k = tk_; h->last_t = se.t; h->last_tld = (se.t + 3) & ~3; h->last_lam_inv = 1.0 / se.lambda_min;
+    } else {
+        h->last_k = 0; h->last_t = 0; h->last_tld = 0;
+    }
     if (status) *status = st;
     if (niter) *niter = nit;
     if (term_k) *term_k = tk_;
@@ -1554,71 +1805,182 @@ int tk_solve(tk_handle* h, double tol, int32_t* status, int64_t* niter, int32_t*
 
 int tk_solution_rank(tk_handle* h, int32_t* t) {
     if (!h || !t) return set_error(TK_EINVAL, "null argument");
-    *t = h->last_t;
+    *t = h->last_t;       // rank of the iterate the getters below return (after tk_solve: the iteration it left at)
     return 0;
 }
 
-int tk_get_solution(tk_handle* h, int32_t s, double* lambda, double* fmat, int32_t force) {
-    bool local = false;
-    TK_TRY(check_mode(h, s, &local));
+}  // extern "C"
+
+namespace tk {
+
+// which iterate the solution getters return, and whether they may
+static int solution_state(tk_handle* h, int32_t force, int* k, int* t, int* tld) {
     if (h->last_k < 2) return set_error(TK_ESTATE, "no compressed solution available");
-    TK_CUDA(cudaSetDevice(h->device));
     int st = ST_RUNNING;
     TK_CUDA(cudaMemcpy(&st, h->status_d.p, sizeof(int), cudaMemcpyDeviceToHost));
-    if (st != ST_CONVERGED && !force) return set_error(TK_ESTATE, "solve did not converge (status %d); pass force to read the last iterate", st);
-    int k = h->last_k;
-    if (st != ST_RUNNING) {
-        int tk_ = 0;
-        TK_CUDA(cudaMemcpy(&tk_, h->term_k_d.p, sizeof(int), cudaMemcpyDeviceToHost));
-        if (tk_ >= 2) k = std::min(k, tk_);
-    }
+    if (st != ST_CONVERGED && !force)
+        return set_error(TK_ESTATE, "solve did not converge (status %d); pass force to read the last iterate", st);
+    *k = h->last_k; *t = h->last_t; *tld = h->last_tld;
+    return 0;
+}
+
+static void solution_lambda(const tk_handle* h, int k, int t, double* lambda) {
     const SchedEntry& se = h->sched[k];
-    const int t = se.t, tld = (t + 3) & ~3;
-    if (lambda) {
-        const double lam_inv = 1.0 / se.lambda_min;
-        for (int j = 0; j < t; ++j) lambda[j] = lam_inv * h->omega_pool[se.off + j];   // y.lambda, tensor_krylov_method.jl:23
-    }
-    if (!local || !fmat) return 0;
-    const int sl = s - h->first;
-    DevBuf<double> X;
-    TK_TRY(X.alloc((size_t)h->n * t, false));
-    dim3 grid((h->n + 255) / 256, (t + BM_TJ - 1) / BM_TJ);
-    const size_t smem = (size_t)k * BM_TJ * 8;
-    basis_mul_kernel<<<grid, 256, smem, h->stream>>>(h->V.p + (size_t)sl * h->ncol * h->ldv, h->ldv, h->n, k,
-                                                     h->Y.p + (size_t)sl * h->ystride, tld, t, X.p);
+    const double lam_inv = 1.0 / se.lambda_min;
+    for (int j = 0; j < t; ++j) lambda[j] = lam_inv * h->omega_pool[se.off + j];   // y.lambda, tensor_krylov_method.jl:23
+}
+
+// basis_tensor_mul! for local modes [m0, m0 + nm) into X ([mode][t][n]) on `st`
+static int launch_basis_mul(tk_handle* h, int k, int t, int tld, int m0, int nm, double* X, cudaStream_t st) {
+    if (nm <= 0) return 0;
+    const int TJ = t <= 8 ? 8 : t <= 16 ? 16 : 32;
+    dim3 grid((h->n + 255) / 256, nm, (t + TJ - 1) / TJ);
+    const size_t smem = (size_t)k * TJ * 8;
+#define TK_BM_LAUNCH(T_)                                                                                         \
+    do {                                                                                                         \
+        TK_TRY(allow_smem(basis_mul_all_kernel<T_>, smem));                                                      \
+        basis_mul_all_kernel<T_><<<grid, 256, smem, st>>>(h->V.p, (long long)h->ncol * h->ldv, h->ldv, h->n, k,  \
+                                                          h->Y.p, h->ystride, tld, t, X, m0);                    \
+    } while (0)
+    if (TJ == 8) TK_BM_LAUNCH(8); else if (TJ == 16) TK_BM_LAUNCH(16); else TK_BM_LAUNCH(32);
+#undef TK_BM_LAUNCH
     TK_CUDA(cudaGetLastError());
-    TK_CUDA(cudaMemcpyAsync(fmat, X.p, 8 * (size_t)h->n * t, cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+
+static bool host_pointer_is_pinned(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+// Factor matrices of local modes [m0, m0 + nm) to host memory: the modes are cut into chunks, chunk c+1 is computed
+// while chunk c crosses PCIe.  Pinned destinations (tk_alloc_host) are written by DMA directly; pageable ones go
+// through two pinned staging buffers and a host copy.
+static int solution_to_host(tk_handle* h, int k, int t, int tld, int m0, int nm, double* fmat) {
+    if (nm <= 0) return 0;
+    tk_resources* r = h->res;
+    const size_t per_mode = (size_t)h->n * t;                      // doubles
+    const size_t chunk_bytes_target = (size_t)std::max(1, env_int("TK_SOL_CHUNK_MB", 32)) << 20;
+    const int cm = (int)std::max<size_t>(1, std::min<size_t>((size_t)nm, chunk_bytes_target / (per_mode * 8)));
+    const bool pinned = host_pointer_is_pinned(fmat);
+    DevBuf<double> X[2];
+    TK_TRY(X[0].alloc((size_t)cm * per_mode, false));
+    TK_TRY(X[1].alloc((size_t)cm * per_mode, false));
+    if (!pinned && r->stage_bytes < (size_t)cm * per_mode * 8) {
+        for (auto& q : r->stage) { if (q) cudaFreeHost(q); q = nullptr; }
+        r->stage_bytes = 0;
+        for (auto& q : r->stage) TK_CUDA(cudaMallocHost(reinterpret_cast<void**>(&q), (size_t)cm * per_mode * 8));
+        r->stage_bytes = (size_t)cm * per_mode * 8;
+    }
+    const int nch = (nm + cm - 1) / cm;
+    auto drain = [&](int c) -> int {           // pageable destination: staging buffer of chunk c -> caller's memory
+        const int c0 = c * cm, cn = std::min(cm, nm - c0);
+        TK_CUDA(cudaEventSynchronize(r->copy_ev[c & 1]));
+        std::memcpy(fmat + (size_t)c0 * per_mode, r->stage[c & 1], (size_t)cn * per_mode * 8);
+        return 0;
+    };
+    for (int c = 0; c < nch; ++c) {
+        const int c0 = c * cm, cn = std::min(cm, nm - c0), bi = c & 1;
+        if (c >= 2) {
+            TK_CUDA(cudaStreamWaitEvent(h->stream, r->copy_ev[bi], 0));     // X[bi] has left the device
+            if (!pinned) TK_TRY(drain(c - 2));                              // ... and its staging buffer is free again
+        }
+        TK_TRY(launch_basis_mul(h, k, t, tld, m0 + c0, cn, X[bi].p, h->stream));
+        TK_CUDA(cudaEventRecord(r->fill_ev[bi], h->stream));
+        TK_CUDA(cudaStreamWaitEvent(r->s_copy, r->fill_ev[bi], 0));
+        double* dst = pinned ? fmat + (size_t)c0 * per_mode : r->stage[bi];
+        TK_CUDA(cudaMemcpyAsync(dst, X[bi].p, (size_t)cn * per_mode * 8, cudaMemcpyDeviceToHost, r->s_copy));
+        TK_CUDA(cudaEventRecord(r->copy_ev[bi], r->s_copy));
+    }
+    if (!pinned)
+        for (int c = std::max(0, nch - 2); c < nch; ++c) TK_TRY(drain(c));
+    TK_CUDA(cudaStreamSynchronize(r->s_copy));
     TK_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
-int tk_get_solution_all(tk_handle* h, double* lambda, double* fmat, int32_t force) {
-    if (!h) return set_error(TK_EINVAL, "null handle");
-    if (h->last_k < 2) return set_error(TK_ESTATE, "no compressed solution available");
+}  // namespace tk
+
+extern "C" {
+
+int tk_get_solution(tk_handle* h, int32_t s, double* lambda, int32_t lambda_cap, double* fmat, int64_t fmat_cap, int32_t force) {
+    bool local = false;
+    TK_TRY(check_mode(h, s, &local));
     TK_CUDA(cudaSetDevice(h->device));
-    int st = ST_RUNNING, tk_ = 0;
-    TK_CUDA(cudaMemcpy(&st, h->status_d.p, sizeof(int), cudaMemcpyDeviceToHost));
-    TK_CUDA(cudaMemcpy(&tk_, h->term_k_d.p, sizeof(int), cudaMemcpyDeviceToHost));
-    if (st != ST_CONVERGED && !force) return set_error(TK_ESTATE, "solve did not converge (status %d); pass force to read the last iterate", st);
-    int k = h->last_k;
-    if (st != ST_RUNNING && tk_ >= 2) k = std::min(k, tk_);
-    const SchedEntry& se = h->sched[k];
-    const int t = se.t, tld = (t + 3) & ~3;
+    int k, t, tld;
+    TK_TRY(solution_state(h, force, &k, &t, &tld));
     if (lambda) {
-        const double lam_inv = 1.0 / se.lambda_min;
-        for (int j = 0; j < t; ++j) lambda[j] = lam_inv * h->omega_pool[se.off + j];
+        if (lambda_cap < t) return set_error(TK_EINVAL, "lambda holds %d entries, the solution has rank %d (tk_solution_rank)", lambda_cap, t);
+        solution_lambda(h, k, t, lambda);
+    }
+    if (!local || !fmat) return 0;
+    if (fmat_cap < (int64_t)h->n * t) return set_error(TK_EINVAL, "fmat holds %lld doubles, need n*t = %lld", (long long)fmat_cap, (long long)h->n * t);
+    return solution_to_host(h, k, t, tld, s - h->first, 1, fmat);
+}
+
+int tk_get_solution_all(tk_handle* h, double* lambda, int32_t lambda_cap, double* fmat, int64_t fmat_cap, int32_t force) {
+    if (!h) return set_error(TK_EINVAL, "null handle");
+    TK_CUDA(cudaSetDevice(h->device));
+    int k, t, tld;
+    TK_TRY(solution_state(h, force, &k, &t, &tld));
+    if (lambda) {
+        if (lambda_cap < t) return set_error(TK_EINVAL, "lambda holds %d entries, the solution has rank %d (tk_solution_rank)", lambda_cap, t);
+        solution_lambda(h, k, t, lambda);
     }
     if (!fmat || h->dl == 0) return 0;
-    DevBuf<double> X;
-    TK_TRY(X.alloc((size_t)h->dl * h->n * t, false));
-    dim3 grid((h->n + 255) / 256, (t + BM_TJ - 1) / BM_TJ);
-    const size_t smem = (size_t)k * BM_TJ * 8;
-    for (int sl = 0; sl < h->dl; ++sl)
-        basis_mul_kernel<<<grid, 256, smem, h->stream>>>(h->V.p + (size_t)sl * h->ncol * h->ldv, h->ldv, h->n, k,
-                                                         h->Y.p + (size_t)sl * h->ystride, tld, t, X.p + (size_t)sl * h->n * t);
-    TK_CUDA(cudaGetLastError());
-    TK_CUDA(cudaMemcpyAsync(fmat, X.p, 8 * (size_t)h->dl * h->n * t, cudaMemcpyDeviceToHost, h->stream));
+    if (fmat_cap < (int64_t)h->dl * h->n * t)
+        return set_error(TK_EINVAL, "fmat holds %lld doubles, need count*n*t = %lld", (long long)fmat_cap, (long long)h->dl * h->n * t);
+    return solution_to_host(h, k, t, tld, 0, h->dl, fmat);
+}
+
+int tk_get_solution_device(tk_handle* h, double* lambda, int32_t lambda_cap, double* fmat_dev, int64_t fmat_cap, int32_t force) {
+    if (!h) return set_error(TK_EINVAL, "null handle");
+    TK_CUDA(cudaSetDevice(h->device));
+    int k, t, tld;
+    TK_TRY(solution_state(h, force, &k, &t, &tld));
+    if (lambda) {
+        if (lambda_cap < t) return set_error(TK_EINVAL, "lambda holds %d entries, the solution has rank %d (tk_solution_rank)", lambda_cap, t);
+        solution_lambda(h, k, t, lambda);
+    }
+    if (!fmat_dev || h->dl == 0) return 0;
+    if (fmat_cap < (int64_t)h->dl * h->n * t)
+        return set_error(TK_EINVAL, "fmat_dev holds %lld doubles, need count*n*t = %lld", (long long)fmat_cap, (long long)h->dl * h->n * t);
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, fmat_dev) != cudaSuccess || attr.type != cudaMemoryTypeDevice || attr.device != h->device) {
+        cudaGetLastError();
+        return set_error(TK_EINVAL, "fmat_dev is not device memory of CUDA device %d", h->device);
+    }
+    TK_TRY(launch_basis_mul(h, k, t, tld, 0, h->dl, fmat_dev, h->stream));
     TK_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int tk_alloc_host(void** out, int64_t bytes) {
+    if (!out || bytes < 0) return set_error(TK_EINVAL, "bad arguments");
+    TK_CUDA(cudaMallocHost(out, (size_t)std::max<int64_t>(bytes, 1)));
+    return 0;
+}
+
+int tk_free_host(void* p) {
+    if (p) TK_CUDA(cudaFreeHost(p));
+    return 0;
+}
+
+int tk_get_detail(tk_handle* h, int32_t k0, int32_t k1, double* out) {
+    if (!h || !out) return set_error(TK_EINVAL, "null argument");
+    if (k0 < 2 || k1 > h->nmax || k1 < k0) return set_error(TK_EINVAL, "iterations %d..%d outside 2..nmax", k0, k1);
+    TK_CUDA(cudaSetDevice(h->device));
+    TK_CUDA(cudaMemcpy(out, h->detail_d.p + (size_t)k0 * 8, 64 * (size_t)(k1 - k0 + 1), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int tk_get_solve_info(tk_handle* h, int32_t* graphs_launched, double* graph_build_ms, int32_t* peer_exchange, int32_t* segments) {
+    if (!h) return set_error(TK_EINVAL, "null handle");
+    if (graphs_launched) *graphs_launched = h->graphs_launched;
+    if (graph_build_ms) *graph_build_ms = h->graph_build_ms;
+    if (peer_exchange) *peer_exchange = h->px_ready ? 1 : 0;
+    if (segments) *segments = (int)h->segs.size();
     return 0;
 }
 

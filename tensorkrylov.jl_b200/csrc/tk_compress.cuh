@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) tridiag_eig_kernel(const double* __restri
                                                           int k, int rows_per_blk, int ldz, double* theta, int thstride,
                                                           double* Q, long long qstride, int ldq, const int* status,
                                                           int* fail, const int* need) {
-    if (status && *status != ST_RUNNING) return;
+    if (status && !cta_running(status)) return;
     if (need && !need[blockIdx.x]) return;      // fallback role: only the problems the bisection kernel flagged
     extern __shared__ double smem[];
     const int prob = blockIdx.x;
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(MAXT) tridiag_eig_bisect_kernel(const double* 
                                                                   int ncol, int k, int tpe, double* theta, int thstride,
                                                                   double* Q, double* scratch, long long qstride,
                                                                   int ldq, const int* status, int* need) {
-    if (status && *status != ST_RUNNING) return;
+    if (status && !cta_running(status)) return;
     extern __shared__ double smem[];
     __shared__ double red[32];
     __shared__ double tile[32][33];
@@ -409,7 +409,7 @@ constexpr int ASM_TJ = 16;
 __device__ void gram_blocks_body(const CompressParams& p, double* scratch);
 
 __global__ void __launch_bounds__(256, 3) assemble_cp_kernel(CompressParams p) {
-    if (*p.status != ST_RUNNING) return;
+    if (!cta_running(p.status)) return;
     extern __shared__ double smem[];
     const int s = blockIdx.x, k = p.k, t = p.t;
     const int cls = p.per_mode ? s : 0;
@@ -516,7 +516,7 @@ __device__ void gram_blocks_body(const CompressParams& p, double* scratch) {
 }
 
 __global__ void __launch_bounds__(256) gram_blocks_kernel(CompressParams p) {
-    if (*p.status != ST_RUNNING) return;
+    if (!cta_running(p.status)) return;
     __shared__ double scratch[32];
     gram_blocks_body(p, scratch);
 }
@@ -531,14 +531,140 @@ __global__ void __launch_bounds__(256) gram_blocks_kernel(CompressParams p) {
 // modes -> one partial, and partials merge across chunks and across GPUs.
 // partial layout: P0 | Pe | Ph | Peh | Pg (t*t each) | v0 | v1 (t each) | bb | orthS | ...
 // ------------------------------------------------------------------------------------------
+struct FinalizeParams {
+    int k, t, nmax, nparts, fixed_iterations;
+    long long pstride;
+    const double* partials;   // [nparts][pstride], merged in order
+    const double* omega;
+    double lam_inv, lambda_min;
+    const SolveCtl* ctl;      // device copy: tolerance of this solve
+    SolveCtl* hctl;           // pinned host copy: receives the exit (status, term_k, niterations)
+    double* relres; double* projres; double* orth;   // [nmax] ConvergenceData vectors
+    double* detail;           // [nmax+1][8]
+    int* status; long long* niter; int* term_k;
+};
+
+// Exchange of the merged partials between the GPUs of one box without a collective launch: every rank stores its
+// merged partial straight into every peer's receive buffer (peer-mapped device memory, NVLink) and then publishes
+// one flag per peer with system-scope release; the same CTA then acquires the flags of all ranks and runs the final
+// merge.  recv[r] is rank r's buffer [2][world][slot_stride] (two iterations deep: a rank can be at most one
+// iteration ahead of the slowest one, because its next exchange needs everybody's flag of this one), flag[r] is
+// rank r's array of `world` counters; the value published for iteration k of a solve is ctl->epoch + k, which only
+// ever grows, so nothing has to be reset between iterations or solves.
+constexpr int PX_MAX = 8;
+struct PeerExchange {
+    int world, rank;
+    long long slot_stride;
+    double* recv[PX_MAX];
+    unsigned long long* flag[PX_MAX];
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Final merge over the GPUs' partials, r_comp (utils.jl:393), the exits of the loop body
+// (tensor_krylov_method.jl:85-118) and the ConvergenceData entries of iteration k.  Whole CTA.
+__device__ void finalize_body(const FinalizeParams& f, double* scratch) {
+    const int t = f.t, tt = t * t;
+    double hy2 = 0.0, bnd = 0.0;
+    for (int pidx = threadIdx.x; pidx < tt; pidx += blockDim.x) {
+        const int i = pidx % t, j = pidx / t;
+        if (i < j) continue;                       // lower triangles only (i >= j)
+        double P0 = 1.0, Pe = 0.0, Ph = 0.0, Peh = 0.0, Pg = 0.0;
+        for (int c = 0; c < f.nparts; ++c) {
+            const double* B = f.partials + (long long)c * f.pstride;
+            const double B0 = __ldcg(B + pidx), Be = __ldcg(B + tt + pidx), Bh = __ldcg(B + 2 * tt + pidx),
+                         Beh = __ldcg(B + 3 * tt + pidx), Bg = __ldcg(B + 4 * tt + pidx);
+            Peh = fma(Peh, B0, fma(Pe, Bh, fma(Ph, Be, P0 * Beh)));
+            Pe = fma(Pe, B0, P0 * Be);
+            Ph = fma(Ph, B0, P0 * Bh);
+            Pg = fma(Pg, B0, P0 * Bg);
+            P0 *= B0;
+        }
+        const double li = f.lam_inv * f.omega[i], lj = f.lam_inv * f.omega[j];   // y.lambda, tensor_krylov_method.jl:23
+        const double w = (i == j) ? 1.0 : 2.0;
+        hy2 = fma(w * (li * lj), Peh, hy2);
+        bnd = fma(w * (li * lj), Pg, bnd);
+    }
+    hy2 = block_sum(hy2, scratch);
+    bnd = block_sum(bnd, scratch);
+    double ip = 0.0;
+    for (int i = threadIdx.x; i < t; i += blockDim.x) {
+        double v0 = 1.0, v1 = 0.0;
+        for (int c = 0; c < f.nparts; ++c) {
+            const double* B = f.partials + (long long)c * f.pstride + 5 * tt;
+            const double b0 = __ldcg(B + i), b1 = __ldcg(B + t + i);
+            v1 = fma(v1, b0, v0 * b1);
+            v0 *= b0;
+        }
+        ip = fma(f.lam_inv * f.omega[i], v1, ip);
+    }
+    ip = block_sum(ip, scratch);
+    if (threadIdx.x == 0) {
+        double bb = 1.0, orthS = 0.0, bn2 = 1.0;
+        for (int c = 0; c < f.nparts; ++c) {
+            const double* B = f.partials + (long long)c * f.pstride + 5 * tt + 2 * t;
+            bb *= __ldcg(B);
+            const double o = __ldcg(B + 1);
+            if (o >= 0.0) orthS = o;
+            bn2 *= __ldcg(B + 2);
+        }
+        const double b_norm = sqrt(bn2);                       // kronprodnorm(b), tensor_struct.jl:277-281
+        const double hyb = ip * b_norm;                        // utils.jl:365
+        const double r_comp = hy2 - 2.0 * hyb + bb;            // utils.jl:393
+        const int k = f.k;
+        double r_norm = sqrt(bnd + r_comp);                    // utils.jl:441
+        double* D = f.detail + (long long)k * 8;
+        D[0] = hy2; D[1] = hyb; D[2] = bb; D[3] = bnd; D[4] = r_comp; D[5] = r_norm; D[6] = (double)t; D[7] = f.lambda_min;
+        int st = ST_RUNNING;
+        long long nit = f.nmax;
+        if (r_comp != r_comp || bnd != bnd) {
+            st = ST_NAN;
+        } else if (r_comp < 0.0 && !f.fixed_iterations) {
+            st = ST_BREAKDOWN;                                 // utils.jl:395 -> tensor_krylov_method.jl:85-96
+            nit = k - 1;
+            *f.niter = nit;
+        } else {
+            if (r_comp < 0.0) r_norm = sqrt(fmax(bnd + r_comp, 0.0));
+            const double rel = r_norm / b_norm;                // tensor_krylov_method.jl:99
+            f.relres[k - 1] = rel;
+            f.projres[k - 1] = r_comp;
+            f.orth[k - 1] = sqrt(orthS);                       // orthogonality_loss(V_1[:,1:k], k), :103
+            if (!f.fixed_iterations && rel < f.ctl->tol) st = ST_CONVERGED;
+            else if (k == f.nmax) st = ST_NMAX;
+        }
+        if (st != ST_RUNNING) {
+            *f.term_k = k;
+            __threadfence();
+            *f.status = st;
+            if (f.hctl) {                                      // the host polls the pinned copy between segments
+                f.hctl->term_k = k;
+                f.hctl->niter = nit;
+                __threadfence_system();
+                *reinterpret_cast<volatile int*>(&f.hctl->status) = st;
+            }
+        }
+    }
+}
+
 // The CTA that finishes last (ticket counter) merges this GPU's chunk partials, in chunk order, into ONE partial:
-// that is what crosses NVLink (18 KB per GPU at t = 21 instead of one partial per chunk) and what finalize_kernel
-// merges across GPUs.
+// that is what crosses NVLink (18 KB per GPU at t = 21 instead of one partial per chunk).  With fin_here it then
+// goes on to the final merge in the same CTA -- directly on one GPU, after the peer exchange (px.world > 1) on
+// several -- so an iteration needs no separate finalize launch and no collective launch.
 __global__ void __launch_bounds__(256) combine_chunk_kernel(CompressParams p, int dl, int chunk_modes, int chunk_base,
                                                             double* partials, long long pstride, const double* orthS,
-                                                            int mode0_local, unsigned int* ticket, double* merged) {
-    if (*p.status != ST_RUNNING) return;
+                                                            int mode0_local, const double* bnorm2, unsigned int* ticket,
+                                                            double* merged, int fin_here, FinalizeParams f, PeerExchange px) {
+    if (!cta_running(p.status)) return;
     __shared__ unsigned int my_ticket;
+    __shared__ double scratch[32];
+    __shared__ int timed_out;
     const int t = p.t, tt = t * t, k = p.k, tld = p.tld;
     const int q0 = blockIdx.x * chunk_modes - chunk_base, q1 = min(dl, q0 + chunk_modes);
     const int qb = max(q0, 0);
@@ -571,10 +697,11 @@ __global__ void __launch_bounds__(256) combine_chunk_kernel(CompressParams p, in
         P[5 * tt + t + i] = v1;
     }
     if (threadIdx.x == 0) {
-        double bb = 1.0;
-        for (int q = qb; q < q1; ++q) bb *= p.bb[q];
+        double bb = 1.0, bn2 = 1.0;
+        for (int q = qb; q < q1; ++q) { bb *= p.bb[q]; bn2 *= bnorm2[q]; }
         P[5 * tt + 2 * t] = bb;
         P[5 * tt + 2 * t + 1] = (mode0_local >= qb && mode0_local < q1) ? orthS[k - 1] : -1.0;
+        P[5 * tt + 2 * t + 2] = bn2;                    // prod_s b_s.b_s of the chunk, for kronprodnorm(b)
     }
     // ---- last CTA: ordered merge of all chunk partials of this GPU
     __threadfence();
@@ -610,130 +737,115 @@ __global__ void __launch_bounds__(256) combine_chunk_kernel(CompressParams p, in
         merged[5 * tt + t + i] = v1;
     }
     if (threadIdx.x == 0) {
-        double bb = 1.0, oS = -1.0;
+        double bb = 1.0, oS = -1.0, bn2 = 1.0;
         for (int c = 0; c < nparts; ++c) {
             const double* B = partials + (long long)c * pstride + 5 * tt + 2 * t;
             bb *= __ldcg(B);
             const double o = __ldcg(B + 1);
             if (o >= 0.0) oS = o;
+            bn2 *= __ldcg(B + 2);
         }
         merged[5 * tt + 2 * t] = bb;
         merged[5 * tt + 2 * t + 1] = oS;
+        merged[5 * tt + 2 * t + 2] = bn2;
         *ticket = 0u;
     }
+    if (!fin_here) return;
+    __syncthreads();
+    if (px.world > 1) {
+        // ---- peer exchange: my merged partial into slot `rank` of everybody's receive buffer (parity k & 1)
+        const unsigned long long want = (unsigned long long)f.ctl->epoch + (unsigned long long)k;
+        const long long half = (long long)px.world * px.slot_stride;
+        for (int r = 0; r < px.world; ++r) {
+            double* dst = px.recv[r] + (long long)(k & 1) * half + (long long)px.rank * px.slot_stride;
+            for (long long i = threadIdx.x; i < pstride; i += blockDim.x) dst[i] = merged[i];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < px.world) st_release_sys(px.flag[threadIdx.x] + px.rank, want);
+        if (threadIdx.x == 0) timed_out = 0;
+        __syncthreads();
+        if (threadIdx.x < px.world) {
+            const unsigned long long* mine = px.flag[px.rank] + threadIdx.x;
+            const long long t0 = clock64();
+            while (ld_acquire_sys(mine) < want) {
+                if (clock64() - t0 > 20000000000LL) { timed_out = 1; break; }   // ~10 s: a peer died; do not hang the GPU
+                __nanosleep(64);
+            }
+        }
+        __syncthreads();
+        if (timed_out) {
+            if (threadIdx.x == 0) {
+                *f.term_k = k;
+                __threadfence();
+                *f.status = ST_NAN;
+                if (f.hctl) { f.hctl->term_k = k; f.hctl->niter = f.nmax; __threadfence_system(); *reinterpret_cast<volatile int*>(&f.hctl->status) = ST_NAN; }
+            }
+            return;
+        }
+        __threadfence_system();
+        f.partials = px.recv[px.rank] + (long long)(k & 1) * half;
+        f.pstride = px.slot_stride;
+        f.nparts = px.world;
+    }
+    finalize_body(f, scratch);
 }
-
-struct FinalizeParams {
-    int k, t, nmax, nparts, fixed_iterations;
-    long long pstride;
-    const double* partials;   // [nparts][pstride], merged in order
-    const double* omega;
-    double lam_inv, lambda_min, tol;
-    const double* bnorm;      // device scalar kronprodnorm(b)
-    double* relres; double* projres; double* orth;   // [nmax] ConvergenceData vectors
-    double* detail;           // [nmax+1][8]
-    int* status; long long* niter; int* term_k;
-};
 
 __global__ void __launch_bounds__(256) finalize_kernel(FinalizeParams f) {
-    if (*f.status != ST_RUNNING) return;
+    if (!cta_running(f.status)) return;
     __shared__ double scratch[32];
-    const int t = f.t, tt = t * t;
-    double hy2 = 0.0, bnd = 0.0;
-    for (int pidx = threadIdx.x; pidx < tt; pidx += blockDim.x) {
-        const int i = pidx % t, j = pidx / t;
-        if (i < j) continue;                       // lower triangles only (i >= j)
-        double P0 = 1.0, Pe = 0.0, Ph = 0.0, Peh = 0.0, Pg = 0.0;
-        for (int c = 0; c < f.nparts; ++c) {
-            const double* B = f.partials + (long long)c * f.pstride;
-            const double B0 = B[pidx], Be = B[tt + pidx], Bh = B[2 * tt + pidx], Beh = B[3 * tt + pidx], Bg = B[4 * tt + pidx];
-            Peh = fma(Peh, B0, fma(Pe, Bh, fma(Ph, Be, P0 * Beh)));
-            Pe = fma(Pe, B0, P0 * Be);
-            Ph = fma(Ph, B0, P0 * Bh);
-            Pg = fma(Pg, B0, P0 * Bg);
-            P0 *= B0;
-        }
-        const double li = f.lam_inv * f.omega[i], lj = f.lam_inv * f.omega[j];   // y.lambda, tensor_krylov_method.jl:23
-        const double w = (i == j) ? 1.0 : 2.0;
-        hy2 = fma(w * (li * lj), Peh, hy2);
-        bnd = fma(w * (li * lj), Pg, bnd);
-    }
-    hy2 = block_sum(hy2, scratch);
-    bnd = block_sum(bnd, scratch);
-    double ip = 0.0;
-    for (int i = threadIdx.x; i < t; i += blockDim.x) {
-        double v0 = 1.0, v1 = 0.0;
-        for (int c = 0; c < f.nparts; ++c) {
-            const double* B = f.partials + (long long)c * f.pstride + 5 * tt;
-            v1 = fma(v1, B[i], v0 * B[t + i]);
-            v0 *= B[i];
-        }
-        ip = fma(f.lam_inv * f.omega[i], v1, ip);
-    }
-    ip = block_sum(ip, scratch);
-    if (threadIdx.x == 0) {
-        double bb = 1.0, orthS = 0.0;
-        for (int c = 0; c < f.nparts; ++c) {
-            const double* B = f.partials + (long long)c * f.pstride + 5 * tt + 2 * t;
-            bb *= B[0];
-            if (B[1] >= 0.0) orthS = B[1];
-        }
-        const double b_norm = *f.bnorm;
-        const double hyb = ip * b_norm;                        // utils.jl:365
-        const double r_comp = hy2 - 2.0 * hyb + bb;            // utils.jl:393
-        const int k = f.k;
-        double r_norm = sqrt(bnd + r_comp);                    // utils.jl:441
-        double* D = f.detail + (long long)k * 8;
-        D[0] = hy2; D[1] = hyb; D[2] = bb; D[3] = bnd; D[4] = r_comp; D[5] = r_norm; D[6] = (double)t; D[7] = f.lambda_min;
-        int st = ST_RUNNING;
-        if (r_comp != r_comp || bnd != bnd) {
-            st = ST_NAN;
-        } else if (r_comp < 0.0 && !f.fixed_iterations) {
-            st = ST_BREAKDOWN;                                 // utils.jl:395 -> tensor_krylov_method.jl:85-96
-            *f.niter = k - 1;
-        } else {
-            if (r_comp < 0.0) r_norm = sqrt(fmax(bnd + r_comp, 0.0));
-            const double rel = r_norm / b_norm;                // tensor_krylov_method.jl:99
-            f.relres[k - 1] = rel;
-            f.projres[k - 1] = r_comp;
-            f.orth[k - 1] = sqrt(orthS);                       // orthogonality_loss(V_1[:,1:k], k), :103
-            if (!f.fixed_iterations && rel < f.tol) st = ST_CONVERGED;
-            else if (k == f.nmax) st = ST_NMAX;
-        }
-        if (st != ST_RUNNING) {
-            *f.term_k = k;
-            __threadfence();
-            *f.status = st;
-        }
-    }
+    finalize_body(f, scratch);
 }
 
 // ------------------------------------------------------------------------------------------
-// x.fmat[s] = V_s[:,1:k] Y_s   (basis_tensor_mul!, utils.jl:478-488); n x t column-major out.
+// x.fmat[s] = V_s[:,1:k] Y_s   (basis_tensor_mul!, utils.jl:478-488) for a range of modes in ONE launch.
+// grid = (row tiles, modes, column passes); a thread owns one row of the n x t result and keeps TJ of its columns
+// in registers, so with t <= TJ the basis panel V_s[:,1:k] is read exactly once (k*n*8 bytes per mode) and the
+// result written once (t*n*8).  Y_s (k x t, a few KB) sits in shared memory and is read as broadcasts.
+// X: [mode][t][n], i.e. n x t column-major per mode (Julia's Matrix{Float64}).
 // ------------------------------------------------------------------------------------------
-constexpr int BM_TJ = 8;
-__global__ void __launch_bounds__(256) basis_mul_kernel(const double* __restrict__ V, long long ldv, int n, int k,
-                                                        const double* __restrict__ Y, int tld, int t, double* X) {
-    extern __shared__ double ysm[];   // k x BM_TJ
-    const int j0 = blockIdx.y * BM_TJ, tj = min(BM_TJ, t - j0);
-    for (int idx = threadIdx.x; idx < k * BM_TJ; idx += blockDim.x) {
-        const int c = idx / BM_TJ, jj = idx % BM_TJ;
-        ysm[idx] = (jj < tj) ? Y[(long long)c * tld + j0 + jj] : 0.0;
+template <int TJ>
+__global__ void __launch_bounds__(256) basis_mul_all_kernel(const double* __restrict__ V, long long vstride, long long ldv,
+                                                            int n, int k, const double* __restrict__ Y, long long ystride,
+                                                            int tld, int t, double* __restrict__ X, int mode0) {
+    extern __shared__ double ysm[];   // k x TJ
+    const int sl = blockIdx.y, s = mode0 + sl;
+    const int j0 = blockIdx.z * TJ, tj = min(TJ, t - j0);
+    const double* Ys = Y + (long long)s * ystride;
+    for (int idx = threadIdx.x; idx < k * TJ; idx += blockDim.x) {
+        const int c = idx / TJ, jj = idx % TJ;
+        ysm[idx] = (jj < tj) ? Ys[(long long)c * tld + j0 + jj] : 0.0;
     }
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double acc[BM_TJ];
+    const double* Vs = V + (long long)s * vstride + i;
+    double acc[TJ];
 #pragma unroll
-    for (int jj = 0; jj < BM_TJ; ++jj) acc[jj] = 0.0;
-    for (int c = 0; c < k; ++c) {
-        const double v = V[(long long)c * ldv + i];
+    for (int jj = 0; jj < TJ; ++jj) acc[jj] = 0.0;
+    int c = 0;
+    for (; c + 3 < k; c += 4) {          // four basis columns in flight per thread
+        const double v0 = ld_stream1(Vs + (long long)c * ldv), v1 = ld_stream1(Vs + (long long)(c + 1) * ldv),
+                     v2 = ld_stream1(Vs + (long long)(c + 2) * ldv), v3 = ld_stream1(Vs + (long long)(c + 3) * ldv);
+        const double* y0 = ysm + c * TJ;
 #pragma unroll
-        for (int jj = 0; jj < BM_TJ; ++jj) acc[jj] = fma(v, ysm[c * BM_TJ + jj], acc[jj]);
+        for (int jj = 0; jj < TJ; ++jj) acc[jj] = fma(v0, y0[jj], acc[jj]);
+#pragma unroll
+        for (int jj = 0; jj < TJ; ++jj) acc[jj] = fma(v1, y0[TJ + jj], acc[jj]);
+#pragma unroll
+        for (int jj = 0; jj < TJ; ++jj) acc[jj] = fma(v2, y0[2 * TJ + jj], acc[jj]);
+#pragma unroll
+        for (int jj = 0; jj < TJ; ++jj) acc[jj] = fma(v3, y0[3 * TJ + jj], acc[jj]);
     }
+    for (; c < k; ++c) {
+        const double v = ld_stream1(Vs + (long long)c * ldv);
 #pragma unroll
-    for (int jj = 0; jj < BM_TJ; ++jj)
-        if (jj < tj) X[(long long)(j0 + jj) * n + i] = acc[jj];
+        for (int jj = 0; jj < TJ; ++jj) acc[jj] = fma(v, ysm[c * TJ + jj], acc[jj]);
+    }
+    double* Xs = X + ((long long)sl * t + j0) * n + i;
+#pragma unroll
+    for (int jj = 0; jj < TJ; ++jj)
+        if (jj < tj) Xs[(long long)jj * n] = acc[jj];
 }
 
 }  // namespace tk

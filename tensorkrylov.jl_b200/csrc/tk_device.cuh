@@ -105,10 +105,37 @@ __device__ __forceinline__ double apply_row(const OpDesc& op, const double* __re
     return acc;
 }
 
+// Run/skip decision of a whole CTA.  finalize flips the status word from another stream while kernels of later
+// iterations are in flight, so threads that each read the live word could disagree and part of a CTA would miss the
+// barriers below; thread 0 reads it once and every thread takes that reading.
+__device__ __forceinline__ bool cta_running(const int* status) {
+    __shared__ int st_s;
+    if (threadIdx.x == 0) st_s = *reinterpret_cast<const volatile int*>(status);
+    __syncthreads();
+    return st_s == ST_RUNNING;
+}
+
+// Solve-wide control words.  The host writes the pinned copy before it launches the first segment of a solve and
+// reset_kernel brings it into device memory, so launches recorded in a CUDA graph do not carry the tolerance or the
+// solve counter as kernel arguments.  finalize writes the exit back to the pinned copy.
+struct SolveCtl {
+    double tol;
+    long long epoch;        // solve counter * (nmax + 2): base of the per-iteration flags of the peer exchange
+    int status;             // host copy only: exit status once the solve has ended, else ST_RUNNING
+    int term_k;
+    long long niter;
+};
+
 // 16-byte streaming load that does not allocate in L1 (the V panel is read once per launch).
 __device__ __forceinline__ double2 ld_stream2(const double2* p) {
     double2 r;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ double ld_stream1(const double* p) {
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
     return r;
 }
 

@@ -45,7 +45,7 @@ __device__ __forceinline__ double hess_entry(const ExpmParams& p, int slot, int 
 
 // one CTA per matrix m = c*t + j: 1-norm of gamma_j H, scaling, A <- gamma_j H / 2^s
 __global__ void __launch_bounds__(256) expm_setup_kernel(ExpmParams p) {
-    if (*p.status != ST_RUNNING) return;
+    if (!cta_running(p.status)) return;
     __shared__ double scratch[32];
     const int m = blockIdx.x, c = m / p.t, j = m % p.t, k = p.k, ld = p.ld;
     const int slot = p.cls_mode[c];
@@ -145,7 +145,7 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ A, const do
 }
 
 __global__ void __launch_bounds__(256) expm_gemm_kernel(ExpmParams p, GemmJob job) {
-    if (*p.status != ST_RUNNING) return;
+    if (!cta_running(p.status)) return;
     const int m = blockIdx.z;
     int sa = job.a, sb = job.b, sc = job.c;
     if (job.sq_step >= 0) {
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256) expm_fused_kernel(ExpmParams p, double f0
         const int st = *cl.map_shared_rank(&st_sh, 0);
         cl.sync();                       // CTA 0 keeps its copy alive until every peer has read it
         if (st != ST_RUNNING) return;
-    } else if (*p.status != ST_RUNNING) {
+    } else if (!cta_running(p.status)) {
         return;
     }
     __shared__ double As[16][65];
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(256) expm_fused_kernel(ExpmParams p, double f0
 // slot 5 <- c12 I + c13 A + c14 A2 + c15 A3 + c16 A4   (start of the Horner scheme in A4; the three Horner products
 // then go 5 -> 4 -> 5 -> 4, leaving the Taylor polynomial in slot 4 where the squarings start)
 __global__ void __launch_bounds__(256) expm_top_kernel(ExpmParams p, double c0, double c1, double c2, double c3, double c4) {
-    if (*p.status != ST_RUNNING) return;
+    if (!cta_running(p.status)) return;
     const int m = blockIdx.y, k = p.k, ld = p.ld;
     double* rec = p.W + (long long)m * EX_SLOTS * p.mslot;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < ld * ld; idx += gridDim.x * blockDim.x) {
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) expm_top_kernel(ExpmParams p, double c0, 
 // Y_s[r][j] = sum_c E_{cls(s), j}[r, c] * b~_s[c]     (expA * b[s], utils.jl:517); Y row-major [k][tld].
 __global__ void __launch_bounds__(256) expm_apply_kernel(ExpmParams p, int per_mode, const double* bt, double* Y,
                                                          long long ystride, int tld) {
-    if (*p.status != ST_RUNNING) return;
+    if (!cta_running(p.status)) return;
     extern __shared__ double bsm[];
     const int s = blockIdx.x, j = blockIdx.y, k = p.k, ld = p.ld;
     const int m = (per_mode ? s : 0) * p.t + j;

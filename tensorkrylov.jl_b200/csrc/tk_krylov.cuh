@@ -39,6 +39,32 @@ __global__ void __launch_bounds__(512) init_basis_kernel(KrylovParams p, double*
 }
 
 // ------------------------------------------------------------------------------------------
+// Start of a solve: status words, ConvergenceData(nmax) = ones (convergence.jl:11-20), the ticket counters (a solve
+// that ended early may have left kernels half-skipped), and the solve-wide control words from the pinned host copy.
+// One launch instead of a dozen small copies, and recordable in a CUDA graph.
+// ------------------------------------------------------------------------------------------
+struct ResetParams {
+    int* status4;                 // [0] live status word, [1..2] snapshots of the cluster kernels
+    int* term_k; int* eigfail; long long* niter;
+    double* relres; double* projres; double* orth; int nmax;
+    unsigned int* tickets; int ntickets; unsigned int* ticket1;
+    SolveCtl* ctl; const SolveCtl* hctl;
+};
+
+__global__ void __launch_bounds__(256) reset_kernel(ResetParams r) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    for (int i = tid; i < r.nmax; i += nthr) { r.relres[i] = 1.0; r.projres[i] = 1.0; r.orth[i] = 1.0; }
+    for (int i = tid; i < r.ntickets; i += nthr) r.tickets[i] = 0u;
+    if (tid == 0) {
+        r.status4[0] = ST_RUNNING; r.status4[1] = ST_RUNNING; r.status4[2] = ST_RUNNING; r.status4[3] = 0;
+        *r.term_k = 0; *r.eigfail = 0; *r.niter = r.nmax;
+        if (r.ticket1) *r.ticket1 = 0u;
+        r.ctl->tol = r.hctl->tol;
+        r.ctl->epoch = r.hctl->epoch;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // 3-term Lanczos step k for every mode.  CPM CTAs (one thread-block cluster) share a mode and
 // split the rows; the three reductions go through distributed shared memory.
 //   u = A v_k - beta_{k-1} v_{k-1};  H[k,k] = u.v_k;  v^ = u - H[k,k] v_k;  beta = ||v^||
@@ -399,7 +425,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 2 : 1)) gram_row_ke
                                                        unsigned int* tickets, double* vscratch) {
     // wpc = warps that share one column: every column is cut into wpc contiguous segments so all warps of the
     // CTA stream equal amounts, whatever the number of columns.
-    if (*p.status != ST_RUNNING) return;
+    if (!cta_running(p.status)) return;
     extern __shared__ double smem[];
     const int s = mode_base + blockIdx.y, n = p.n;
     const int c0 = blockIdx.x * cols_per_cta, c1 = min(ncols, c0 + cols_per_cta);
@@ -492,6 +518,122 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 2 : 1)) gram_row_ke
 }
 
 // ------------------------------------------------------------------------------------------
+// Balanced form of the Gram row: the nmodes * ncols columns of one launch are ONE list (mode-major), cut into
+// gridDim.x equal contiguous ranges, one per CTA (grid = resident CTAs of the GPU: a single wave, no tail).  The
+// (chunks, modes) grid above quantises badly when a GPU holds few modes (128 per GPU at d = 1024 on 8 GPUs: 256
+// CTAs on 296 slots) or few columns; here every CTA streams the same number of bytes +- one column for any mode
+// and column count.  A CTA re-stages the new vector when its range crosses into the next mode (L2 hits: the 3-term
+// step has just written it).  tickets[s] counts finished COLUMNS of mode s; the CTA that completes a mode runs the
+// monitor.  Same per-column arithmetic (segments, lanes, association order) as gram_row_kernel: bit-identical g.
+// ------------------------------------------------------------------------------------------
+constexpr int GRAM_BATCH = 32;     // columns per pass of a CTA (size of its partial-sum tile)
+
+template <int U, int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 2 : 1)) gram_row_balanced_kernel(KrylovParams p, int ncols, int nmodes,
+                                                                int mode_base, int wpc, int monitor, unsigned int* tickets) {
+    if (!cta_running(p.status)) return;
+    extern __shared__ double smem[];
+    __shared__ double scratch[32];
+    __shared__ unsigned int my_ticket;
+    const int n = p.n, nq = n >> 1;
+    double* part = smem;                                            // [GRAM_BATCH][GRAM_PSTRIDE]
+    double* hcol = smem + GRAM_BATCH * GRAM_PSTRIDE;                // ncol doubles (MGS fallback)
+    double* wsm = hcol + ((p.ncol + 1) & ~1);
+    const long long total = (long long)nmodes * ncols;
+    long long cur = total * blockIdx.x / gridDim.x;
+    const long long end = total * (blockIdx.x + 1) / gridDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = THREADS >> 5;
+    const int seg = warp % wpc, group = warp / wpc, ngroups = nwarp / wpc;
+    const int seglen = (((nq + wpc - 1) / wpc) + 31) & ~31;
+    const int q0 = seg * seglen, q1 = min(nq, q0 + seglen);
+    const double2* w2 = reinterpret_cast<const double2*>(wsm);
+    while (cur < end) {
+        const int sl = (int)(cur / ncols), s = mode_base + sl;
+        const int jfirst = (int)(cur - (long long)sl * ncols);
+        const int jend = (int)min((long long)ncols, jfirst + (end - cur));
+        const double* Vs = p.V + (long long)s * p.vstride;
+        const double* wg = Vs + (long long)(ncols - 1) * p.ldv;
+        __syncthreads();                                            // previous mode's readers of wsm are done
+        {
+            const double2* w2g = reinterpret_cast<const double2*>(wg);
+            double2* s2 = reinterpret_cast<double2*>(wsm);
+            int q = threadIdx.x;
+            for (; q + 3 * THREADS < nq; q += 4 * THREADS) {
+                const double2 t0 = w2g[q], t1 = w2g[q + THREADS], t2 = w2g[q + 2 * THREADS], t3 = w2g[q + 3 * THREADS];
+                s2[q] = t0; s2[q + THREADS] = t1; s2[q + 2 * THREADS] = t2; s2[q + 3 * THREADS] = t3;
+            }
+            for (; q < nq; q += THREADS) s2[q] = w2g[q];
+            if ((n & 1) && threadIdx.x == 0) wsm[n - 1] = wg[n - 1];
+        }
+        __syncthreads();
+        double* g = p.g + (long long)s * p.ncol;
+        for (int c0 = jfirst; c0 < jend; c0 += GRAM_BATCH) {
+            const int c1 = min(jend, c0 + GRAM_BATCH);
+            for (int j = c0 + group; j < c1; j += 2 * ngroups) {
+                const int jb = j + ngroups;
+                const bool two = jb < c1;
+                const double2* ca = reinterpret_cast<const double2*>(Vs + (long long)j * p.ldv);
+                const double2* cb = reinterpret_cast<const double2*>(Vs + (long long)(two ? jb : j) * p.ldv);
+                double a[U], b[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) { a[u] = 0.0; b[u] = 0.0; }
+                int q = q0 + lane;
+                for (; q + 32 * (U - 1) < q1; q += 32 * U) {
+                    double2 x[U], z[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) x[u] = ld_stream2(ca + q + 32 * u);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) z[u] = ld_stream2(cb + q + 32 * u);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const double2 y = w2[q + 32 * u];
+                        a[u] = fma(x[u].x, y.x, a[u]); a[u] = fma(x[u].y, y.y, a[u]);
+                        b[u] = fma(z[u].x, y.x, b[u]); b[u] = fma(z[u].y, y.y, b[u]);
+                    }
+                }
+                for (; q < q1; q += 32) {
+                    const double2 x0 = ld_stream2(ca + q), z0 = ld_stream2(cb + q);
+                    const double2 y0 = w2[q];
+                    a[0] = fma(x0.x, y0.x, a[0]); a[0] = fma(x0.y, y0.y, a[0]);
+                    b[0] = fma(z0.x, y0.x, b[0]); b[0] = fma(z0.y, y0.y, b[0]);
+                }
+                if ((n & 1) && seg == wpc - 1 && lane == 0) {
+                    a[0] = fma(Vs[(long long)j * p.ldv + n - 1], wsm[n - 1], a[0]);
+                    if (two) b[0] = fma(Vs[(long long)jb * p.ldv + n - 1], wsm[n - 1], b[0]);
+                }
+                double sa = 0.0, sb = 0.0;
+#pragma unroll
+                for (int u = 0; u < U; ++u) { sa += a[u]; sb += b[u]; }
+                sa = warp_sum(sa);
+                sb = warp_sum(sb);
+                if (lane == 0) {
+                    part[(j - c0) * GRAM_PSTRIDE + seg] = sa;
+                    if (two) part[(jb - c0) * GRAM_PSTRIDE + seg] = sb;
+                }
+            }
+            __syncthreads();
+            for (int j = c0 + threadIdx.x; j < c1; j += THREADS) {
+                double acc = 0.0;
+                for (int sgi = 0; sgi < wpc; ++sgi) acc += part[(j - c0) * GRAM_PSTRIDE + sgi];
+                g[j] = acc;
+            }
+            __syncthreads();
+        }
+        cur += jend - jfirst;
+        if (monitor < 0) continue;
+        // the CTA that completes the row of this mode folds it into S (and runs the MGS fallback if needed)
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) my_ticket = atomicAdd(tickets + s, (unsigned int)(jend - jfirst));
+        __syncthreads();
+        if (my_ticket + (unsigned int)(jend - jfirst) != (unsigned int)ncols) continue;
+        __threadfence();
+        monitor_body(p, s, ncols - 1, monitor, hcol, wsm, scratch);
+        if (threadIdx.x == 0) tickets[s] = 0u;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Register-resident Arnoldi step: same two-pass MGS in the reference's order, but the working vector lives in
 // registers (EPT rows per thread), each basis column is fetched ONCE per pass (the dot and the update use the same
 // registers), the next PD columns are already in flight while the current one is being reduced, and the block reduction
@@ -500,7 +642,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 2 : 1)) gram_row_ke
 // ------------------------------------------------------------------------------------------
 template <int EPT, int THREADS, int PD>   // PD: basis columns kept in flight ahead of the one being reduced (0, 1 or 3)
 __global__ void __launch_bounds__(THREADS) arnoldi_mgs_reg_kernel(KrylovParams p, int k) {
-    if (*p.status != ST_RUNNING) return;
+    if (!cta_running(p.status)) return;
     extern __shared__ double hcol[];                    // k+1
     __shared__ double scr[2][32];
     const int s = blockIdx.x, n = p.n, tid = threadIdx.x;
@@ -592,7 +734,7 @@ __global__ void __launch_bounds__(THREADS) arnoldi_mgs_reg_kernel(KrylovParams p
 // the Hessenberg matrix.  Algorithmic HBM bytes per mode: (16 k + 8 (ndiag + 3)) n.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512) arnoldi_mgs_kernel(KrylovParams p, int k, double* vscratch) {
-    if (*p.status != ST_RUNNING) return;
+    if (!cta_running(p.status)) return;
     extern __shared__ double smem[];
     __shared__ double scratch[32];
     const int s = blockIdx.x;

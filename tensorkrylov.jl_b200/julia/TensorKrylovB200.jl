@@ -110,8 +110,9 @@ function tensorkrylov_b200!(convergence_data::ConvergenceData{T}, A::KronMat{mat
             t = Int(tref[])
             x = KruskalTensor{T}(ones(t), [zeros(Int(ns[s]), t) for s in 1:d])
             for s in 1:d
-                check(ccall((:tk_get_solution, libtk), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Int32),
-                            h, s - 1, x.lambda, x.fmat[s], 0))
+                check(ccall((:tk_get_solution, libtk), Cint,
+                            (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Ptr{Float64}, Int64, Int32),
+                            h, s - 1, x.lambda, length(x.lambda), x.fmat[s], length(x.fmat[s]), 0))
             end
             println("Convergence")
             return x

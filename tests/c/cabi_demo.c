@@ -66,7 +66,7 @@ int main(int argc, char** argv) {
     CHECK(tk_solution_rank(h, &t));
     double* lambda = malloc(sizeof(double) * (t > 0 ? t : 1));
     double* fmat = malloc(sizeof(double) * n * (t > 0 ? t : 1));
-    CHECK(tk_get_solution(h, d - 1, lambda, fmat, 1));
+    CHECK(tk_get_solution(h, d - 1, lambda, t, fmat, (int64_t)n * t, 1));
     printf("solution t %d lambda0 %.17g f00 %.17g\n", t, lambda[0], fmat[0]);
     tk_destroy(h);
     CHECK(tk_release_cache());

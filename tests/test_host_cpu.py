@@ -271,8 +271,11 @@ def test_argument_validation_needs_no_gpu(tk):
     assert lib.tk_set_schedule(None, 2, 1.0, 1, capi.dptr(z), capi.dptr(z)) == EINVAL
     assert lib.tk_schedule_laplace(None, 1e-8) == EINVAL
     assert lib.tk_local_modes(None, C.byref(i32), C.byref(i32)) == EINVAL
-    assert lib.tk_get_solution(None, 0, capi.dptr(z), capi.dptr(z), 0) == EINVAL
-    assert lib.tk_get_solution_all(None, capi.dptr(z), capi.dptr(z), 0) == EINVAL
+    assert lib.tk_get_solution(None, 0, capi.dptr(z), 8, capi.dptr(z), 8, 0) == EINVAL
+    assert lib.tk_get_solution_all(None, capi.dptr(z), 8, capi.dptr(z), 8, 0) == EINVAL
+    assert lib.tk_get_solution_device(None, capi.dptr(z), 8, None, 8, 0) == EINVAL
+    assert lib.tk_get_detail(None, 2, 2, capi.dptr(z)) == EINVAL
+    assert lib.tk_get_solve_info(None, None, None, None, None) == EINVAL
     assert lib.tk_launch_count(None, C.byref(i64)) == EINVAL
     assert lib.tk_begin(None) == EINVAL
     assert lib.tk_step_bases(None, 2) != 0 and lib.tk_compress(None, 2) != 0 and lib.tk_residual(None, 2, 0.0, None) != 0
