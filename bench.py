@@ -1,19 +1,23 @@
 #!/usr/bin/env python3
 """bench.py -- Krylov iterations/s of the tensorized solve on B200 (BASELINE.json metric).
 
-Workload (config 5 of BASELINE.json): d = 1024 modes, n_s = 10^4, 1D Laplacian per mode,
-rank-1 right-hand side (one U(0,1) vector for all modes, seed 12345, normalised),
-TensorLanczosReorth, exp-sum schedule from the coefficient tables at tol 1e-8, reference
-semantics (exp(gamma H_1) for all modes), fixed-iteration mode (nmax-1 Krylov iterations per
-solve; BASELINE.md: no reference run reaches its tolerance, throughput is quoted per iteration).
+Default workload = config 5 of BASELINE.json: d = 1024 modes, n_s = 10^4, 1D Laplacian per mode, rank-1
+right-hand side (one U(0,1) vector for all modes, seed 12345, normalised), TensorLanczosReorth, exp-sum
+schedule from the coefficient tables at tol 1e-8, reference semantics (exp(gamma H_1) for all modes),
+fixed-iteration mode (nmax-1 Krylov iterations per solve; BASELINE.md: no reference run reaches its tolerance,
+throughput is quoted per iteration).  `--config C1..C4` selects the other configurations of BASELINE.json,
+`--nmax`, `--t-override` and `--weak` the sweeps of config 5 (tools/run_sweeps.sh writes them to profiles/).
 
-A "step" is one whole solve.  value = Krylov iterations (all d modes advanced) per second, timed
-with CUDA events on the library's stream, max over ranks.  With --gpus N the d modes are
-block-partitioned over N ranks (strong scaling), one NCCL all-gather + one 3*(nmax+1)-double
-broadcast per iteration.
+A "step" is one whole solve.  value = Krylov iterations (all d modes advanced) per second over K solves of a
+resident handle, timed on the device (CUDA events on the library's stream), max over ranks; no per-kernel events
+in that pass.  The roofline numbers come from a second pass over the same K solves with events around the
+Krylov-step kernels.  With --gpus N the d modes are block-partitioned over N ranks (strong scaling; --weak: 128
+modes per GPU); per iteration the ranks exchange one merged partial each (peer-mapped stores, NCCL as fallback).
 
-`--impl reference` times the CPU oracle (the reference is Julia, which this image does not have)
-on the host cores on a bounded sample of the same workload.
+`parity`: iterations 2..16 of the timed solve (||Hy||^2, <Hy,b>, ||b~||^2, boundary, r_comp, relres) against the
+oracle fixture tests/golden/c{3,5}_oracle.npz, at every N; a miss makes the run exit non-zero.
+
+`--impl reference` times the CPU oracle (the reference is Julia, which this image does not have) on the host cores.
 """
 import argparse
 import json
@@ -33,6 +37,14 @@ import __graft_entry__ as entry  # noqa: E402
 METRIC = "krylov_iters_per_s"
 UNIT = "iter/s"
 
+CONFIGS = {   # BASELINE.json configs; nmax per SURVEY.md 8 (the reference's n-1 / n is infeasible at n = 10^4)
+    "C1": dict(d=5, n=200, cls="Laplace", variant="reorth", nmax=199),
+    "C2": dict(d=50, n=1000, cls="Laplace", variant="reorth", nmax=256),
+    "C3": dict(d=256, n=10000, cls="Laplace", variant="reorth", nmax=64),
+    "C4": dict(d=100, n=2000, cls="ConvDiff", variant="arnoldi", nmax=120),
+    "C5": dict(d=1024, n=10000, cls="Laplace", variant="reorth", nmax=64),
+}
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -40,21 +52,35 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--d", type=int, default=1024)
-    ap.add_argument("--n", type=int, default=10000)
-    ap.add_argument("--nmax", type=int, default=64)
+    ap.add_argument("--config", default="C5", choices=sorted(CONFIGS))
+    ap.add_argument("--d", type=int, default=None)
+    ap.add_argument("--n", type=int, default=None)
+    ap.add_argument("--nmax", type=int, default=None)
     ap.add_argument("--tol", type=float, default=1e-8)
-    ap.add_argument("--variant", default="reorth", choices=["reorth", "lanczos"])
+    ap.add_argument("--variant", default=None, choices=["reorth", "lanczos", "arnoldi"])
     ap.add_argument("--per-mode", action="store_true", help="each mode exponentiates its own H_s (not the reference's H_1)")
-    ap.add_argument("--cpu-sample-modes", type=int, default=512)
+    ap.add_argument("--t-override", type=int, default=0, help="exp-sum rank used at every iteration (sweep of config 5)")
+    ap.add_argument("--weak", action="store_true", help="weak scaling: d = 128 * gpus")
+    ap.add_argument("--cpu-sample-modes", type=int, default=0, help="modes the CPU arm advances (0 = all d: no scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-extras", action="store_true", help="skip time-to-tol and the end-to-end arm (sweeps)")
+    a = ap.parse_args()
+    c = CONFIGS[a.config]
+    a.cls = c["cls"]
+    a.d = a.d or (128 * a.gpus if a.weak else c["d"])
+    a.n = a.n or c["n"]
+    a.nmax = a.nmax or c["nmax"]
+    a.variant = a.variant or c["variant"]
+    return a
 
 
 def workload_name(a):
-    tag = "C5" if (a.d, a.n, a.nmax) == (1024, 10000, 64) else "custom"
-    return (f"{tag} d={a.d} n={a.n} Laplace TensorLanczos{'Reorth' if a.variant == 'reorth' else ''} nmax={a.nmax} "
-            f"tol={a.tol:g} fixed-iterations {'per-mode H_s' if a.per_mode else 'reference H_1'}")
+    c = CONFIGS[a.config]
+    tag = a.config if (a.d, a.n, a.nmax, a.variant) == (c["d"], c["n"], c["nmax"], c["variant"]) and not a.t_override else a.config + "-variant"
+    var = {"reorth": "TensorLanczosReorth", "lanczos": "TensorLanczos", "arnoldi": "TensorArnoldi"}[a.variant]
+    extra = f" t={a.t_override}" if a.t_override else ""
+    return (f"{tag} d={a.d} n={a.n} {a.cls} {var} nmax={a.nmax} tol={a.tol:g}{extra} fixed-iterations "
+            f"{'per-mode H_s' if a.per_mode else 'reference H_1'}")
 
 
 class ClockSampler:
@@ -143,13 +169,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
-def measured_traffic_ratio():
-    """DRAM bytes / algorithmic bytes of the Gram-row kernel from the committed `ncu --set full` capture."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_gram_traffic.json")))
-        return float(t["traffic_over_algorithmic"]), "profiles/r01_gram_traffic.json (ncu dram__bytes_read+write, launches with 31-33 columns)"
-    except Exception:
-        return None, None
+def measured_traffic_ratio(kind):
+    """DRAM bytes / algorithmic bytes of the dominant kernel from the committed `ncu --set full` capture."""
+    for name in (f"r02_{kind}_traffic.json", f"r01_{kind}_traffic.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))
+            return float(t["traffic_over_algorithmic"]), f"profiles/{name} (ncu dram__bytes_read+write per launch)"
+        except Exception:
+            continue
+    return None, None
 
 
 def measured_peak():
@@ -160,39 +188,64 @@ def measured_peak():
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU arm: the oracle port on the host cores, bounded sample of the same workload
+# parity of the timed solve against the oracle fixture
+# ---------------------------------------------------------------------------------------------
+def parity_check(a, detail, relres):
+    """Iterations 2..16 of the benchmarked solve against tests/golden/c{3,5}_oracle.npz (tolerance model of
+    SURVEY.md 8c: terms 1e-11 relative, boundary 1e-10, r_comp 1e-11 of the terms it cancels, relres^2 4e-11)."""
+    name = {(256, 10000): "c3", (1024, 10000): "c5"}.get((a.d, a.n))
+    if (name is None or a.cls != "Laplace" or a.variant != "reorth" or a.per_mode or a.t_override or a.tol != 1e-8
+            or a.nmax < 16):
+        return {"checked": False, "why": "no oracle fixture for this workload (fixtures: C3 and C5 as configured)"}
+    ref = np.load(os.path.join(ROOT, "tests", "golden", name + "_oracle.npz"))
+    ks = ref["k"]
+    m = len(ks)
+    worst = {}
+    for key in ("hy2", "hyb", "bb", "boundary"):
+        worst[key] = float((np.abs(detail[key][:m] - ref[key]) / np.abs(ref[key])).max())
+    scale = np.abs(ref["hy2"]) + 2 * np.abs(ref["hyb"]) + np.abs(ref["bb"])
+    worst["r_comp_over_terms"] = float((np.abs(detail["r_comp"][:m] - ref["r_comp"]) / scale).max())
+    worst["relres_sq_abs"] = float(np.abs(relres[ks - 1] ** 2 - ref["relres"][ks - 1] ** 2).max())
+    ok = (max(worst["hy2"], worst["hyb"], worst["bb"], worst["r_comp_over_terms"]) < 1e-11 and worst["boundary"] < 1e-10
+          and worst["relres_sq_abs"] < 4e-11 and np.array_equal(detail["t"][:m].astype(int), ref["t"]))
+    return {"checked": True, "ok": bool(ok), "fixture": f"tests/golden/{name}_oracle.npz", "iterations": [int(ks[0]), int(ks[-1])],
+            "worst": worst, "relres_k16": float(relres[15]), "relres_k16_oracle": float(ref["relres"][15])}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
 # ---------------------------------------------------------------------------------------------
 def cpu_arm(a, sample_modes):
     """Times the oracle (flavour B of BASELINE.md: one eigendecomposition per iteration and the O(d t^2) combine,
-    i.e. the GPU path's algorithm; the reference's own O(d^3 t^2) loops cannot run at d = 1024) on
-    `sample_modes` of the d modes for all nmax-1 iterations.  Per-iteration cost is linear in the number of
-    modes, so iterations/s at d modes = (nmax-1) / (t_sample * d / sample_modes)."""
+    i.e. the GPU path's algorithm; the reference's own O(d^3 t^2) loops cannot run at d = 1024) for all nmax-1
+    iterations.  sample_modes = 0 advances all d modes (nothing is scaled); otherwise `sample_modes` of them, and
+    iterations/s at d modes = (nmax-1) / (t_sample * d / sample_modes) -- per-iteration cost is linear in d."""
     orc = entry.load_oracle()
-    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
-    threads = os.cpu_count()
-    tk_tables = os.path.join(entry.PKG_DIR, "data", "expsum_tables.bin")
-    tables = orc.ExpSumTables.from_packed(tk_tables)
-    ds = min(sample_modes, a.d)
-    A = orc.assemble_matrix(a.n, orc.LAPLACE)
+    threads = os.cpu_count()     # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
+    tables = orc.ExpSumTables.from_packed(os.path.join(entry.PKG_DIR, "data", "expsum_tables.bin"))
+    ds = a.d if sample_modes <= 0 else min(sample_modes, a.d)
+    cls = {"Laplace": orc.LAPLACE, "ConvDiff": orc.CONVDIFF}[a.cls]
+    inst = orc.NONSYM if a.variant == "arnoldi" else orc.SYM
+    A = orc.assemble_matrix(a.n, cls)
     b = orc.normalize_rhs(orc.random_rhs(ds, a.n, 12345))
-    sched = orc.build_schedule(A, a.d, a.nmax, a.tol, orc.SYM, orc.LAPLACE, tables)
-    variant = orc.LANCZOS_REORTH if a.variant == "reorth" else orc.LANCZOS
+    sched = orc.build_schedule(A, a.d, a.nmax, a.tol, inst, cls, tables)
+    variant = {"reorth": orc.LANCZOS_REORTH, "lanczos": orc.LANCZOS, "arnoldi": orc.ARNOLDI}[a.variant]
     t0 = time.perf_counter()
-    # one worker thread per core over the (independent) modes, BLAS itself single-threaded inside each worker
     try:
         from threadpoolctl import threadpool_limits
-        threadpool_limits(limits=1)
+        threadpool_limits(limits=1)   # one worker thread per core over the (independent) modes, BLAS single-threaded inside
     except Exception:
         pass
-    S = orc.OracleSolve([A] * ds, b, a.tol, a.nmax, variant, orc.SYM, orc.LAPLACE, tables, per_mode=a.per_mode,
+    S = orc.OracleSolve([A] * ds, b, a.tol, a.nmax, variant, inst, cls, tables, per_mode=a.per_mode,
                         residual="nilpotent", fast_solve=True, schedule=sched, ignore_breakdown=True,
                         mode_threads=threads)
     S.run()
     dt = time.perf_counter() - t0
     its = (a.nmax - 1) / (dt * a.d / ds)
+    how = "all modes, nothing scaled" if ds == a.d else f"{ds} of {a.d} modes, scaled linearly in d"
     return {"value": its, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{ds} of {a.d} modes x {a.nmax - 1} iterations in {dt:.1f} s, scaled linearly in d; numpy/scipy, "
-                      f"{threads} worker threads over the modes; oracle flavour B (GPU-matched algorithm)"}, dt
+            "sample": f"{how}; {a.nmax - 1} iterations in {dt:.1f} s; numpy/scipy, {threads} worker threads over the "
+                      f"modes; oracle flavour B (the GPU path's algorithm: the reference's O(d^3 t^2) loops cannot run at this d)"}, dt
 
 
 def run_reference(a):
@@ -200,19 +253,21 @@ def run_reference(a):
     if rank != 0:
         return 0
     vals, dts = [], []
-    for _ in range(max(a.warmup, 0) and 1):
-        cpu_arm(a, max(4, a.cpu_sample_modes // 8))
+    if a.warmup > 0:
+        cpu_arm(a, max(4, a.d // 64))
     for _ in range(max(a.steps, 1)):
         cb, dt = cpu_arm(a, a.cpu_sample_modes)
         vals.append(cb["value"]); dts.append(dt)
-        if sum(dts) > 150:
+        if sum(dts) > 150:       # bounded: the whole arm stays within a few minutes
             break
     v = float(np.mean(vals))
     cb["value"] = v
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": len(vals),
-            "warmup": a.warmup, "ms_per_step": 1e3 * (a.nmax - 1) / v, "higher_is_better": True, "scaling": "strong",
+            "warmup": a.warmup, "ms_per_step": 1e3 * (a.nmax - 1) / v, "higher_is_better": True,
+            "scaling": "weak" if a.weak else "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "note": "Julia is not installed; the CPU arm is the oracle port"},
+            "config": {"workload": workload_name(a), "note": "Julia is not installed; the CPU arm is the oracle port; "
+                       f"{len(vals)} whole solves were timed (150 s budget)"},
             "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -251,23 +306,30 @@ def run_b200(a):
         uid = bytes(buf.cpu().numpy().tobytes())
 
     d, n, nmax = a.d, a.n, a.nmax
-    variant = tk.TensorLanczosReorth if a.variant == "reorth" else tk.TensorLanczos
+    variant = {"reorth": tk.TensorLanczosReorth, "lanczos": tk.TensorLanczos, "arnoldi": tk.TensorArnoldi}[a.variant]
+    instance = tk.NonSymInstance if a.variant == "arnoldi" else tk.SymInstance
+    cls = getattr(tk, a.cls)
     base = tk.TK_FLAG_FIXED_ITERATIONS | (0 if a.per_mode else tk.TK_FLAG_REFERENCE_H1)
-    A1 = tk.assemble_matrix(n, tk.Laplace)
+    A1 = tk.assemble_matrix(n, cls)
     # pinned host buffers: the step's inputs
     b_host = torch.from_numpy(np.random.default_rng(12345).random(n)).pin_memory()
     b_np = b_host.numpy()
     b_np *= 1.0 / np.linalg.norm(b_np)        # TensorizedSystem normalises b (system.jl:33-37)
 
     def make(flags):
-        s = tk.Solver(d, n, nmax, tk.SymInstance, tk.Laplace, variant, flags=flags, device=local, rank=rank,
-                      world=world, unique_id=uid)
-        return s
+        return tk.Solver(d, n, nmax, instance, cls, variant, flags=flags, device=local, rank=rank, world=world, unique_id=uid)
 
-    def feed(s):
+    def feed(s, tol=None):
         s.set_operators([A1] * d)
         s.set_rhs([b_np] * d)
-        s.set_schedule(A1, a.tol)
+        if a.t_override:
+            # the rank sweep of config 5: the coefficient file of rank t in the table row of every iteration's kappa
+            for k in range(2, nmax + 1):
+                lmin, lmax = tk.extreme_eigvals(A1, d, k, instance, cls)
+                om, al, _ = tk.sym_rank_coefficients(lmax * (1.0 / lmin), a.t_override)
+                s.set_schedule_entry(k, lmin, al, om)
+        else:
+            s.set_schedule(A1, a.tol if tol is None else tol)
 
     def barrier():
         if world > 1:
@@ -281,83 +343,137 @@ def run_b200(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident arm: inputs already in HBM, handle reused; kernel events on -------
-    slv = make(base | tk.TK_FLAG_TIME_KERNELS)
+    # ---- device-resident arm: inputs already in HBM, handle reused, no per-kernel events: the headline `value` --
+    slv = make(base)
     feed(slv)
-    for _ in range(a.warmup):
+    for _ in range(max(a.warmup, 3)):
         slv.solve(a.tol)
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
         sampler.start()
-    dev_ms, gram_ms, gram_bytes, gram_n, ttr_ms, ttr_bytes, launches = 0.0, 0.0, 0.0, 0, 0.0, 0.0, 0
+    launches = 0
     slv.timing_mark()               # CUDA event on the library's stream: start of the K-step timed region
     t0 = time.perf_counter()
     for _ in range(a.steps):
         res = slv.solve(a.tol)
-        ms, cnt, by = slv.timing(1)
-        gram_ms += ms; gram_n += cnt; gram_bytes += by
-        ms, cnt, by = slv.timing(0)
-        ttr_ms += ms; ttr_bytes += by
         launches += slv.launch_count()
     dev_ms = slv.timing(7)[0]       # region start -> end of the last solve, on the device
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
     clocks = sampler.stop() if rank == 0 else None
     dev_ms = maxr(dev_ms)
-    gram_ms = maxr(gram_ms)
+    info = slv.solve_info()
     relres_last = float(res["relres"][nmax - 1])
     status = res["status"]
+    parity = parity_check(a, slv.detail(2, min(nmax, 16)), res["relres"]) if nmax >= 2 else {"checked": False}
     fb = slv.orth_state(slv.first)[1] if slv.count else 0
     slv.close()
 
-    # ---- time-to-tolerance (second half of BASELINE.json's metric): parity mode, tol 1e-5 -- the only tolerance
-    # this configuration reaches: device time from first enqueue to the converged status
-    ttt = None
-    if a.d >= 256 and a.n >= 10000:
-        s2 = make(0 if a.per_mode else tk.TK_FLAG_REFERENCE_H1)
-        s2.set_operators([A1] * d); s2.set_rhs([b_np] * d); s2.set_schedule(A1, 1e-5)
-        best = None
-        for _ in range(3):
-            barrier()
-            t0 = time.perf_counter()
-            r2 = s2.solve(1e-5)
-            wall = 1e3 * (time.perf_counter() - t0)
-            dev = maxr(s2.timing(6)[0])
-            if best is None or dev < best[0]:
-                best = (dev, wall)
-        ttt = {"tol": 1e-5, "status": r2["status"], "iterations": r2["term_k"], "device_ms": best[0], "call_ms": best[1],
-               "relres": float(r2["relres"][r2["term_k"] - 1]) if r2["term_k"] >= 1 else None}
-        s2.close()
-
-    # ---- end-to-end arm: the public call with host buffers, H2D and D2H inside the timed region -----
-    A = tk.KroneckerMatrix(tk.SymInstance, [A1] * d, tk.Laplace)
-    def e2e_once():
-        out = []
-        cd = tk.ConvergenceData(nmax)
-        s = make(base)
-        try:
-            feed(s)
-            r = s.solve(a.tol)
-            cd.relative_residual_norm[:] = r["relres"]
-        finally:
-            s.close()
-        return cd
-    for _ in range(min(a.warmup, 2)):
-        e2e_once()
+    # ---- instrumented pass: the same K solves with CUDA events around the Krylov-step kernels (stream launches) --
+    kind = 2 if a.variant == "arnoldi" else 1
+    slv = make(base | tk.TK_FLAG_TIME_KERNELS)
+    feed(slv)
+    for _ in range(2):
+        slv.solve(a.tol)
     barrier()
-    t0 = time.perf_counter()
+    top_ms = top_bytes = ttr_ms = ttr_bytes = 0.0
+    top_n = 0
+    slv.timing_mark()
     for _ in range(a.steps):
-        cd = e2e_once()
-    barrier()
-    e2e_ms = maxr(1e3 * (time.perf_counter() - t0))
-    assert abs(cd.relative_residual_norm[nmax - 1] - relres_last) <= 1e-9 * abs(relres_last) + 1e-300
+        res_i = slv.solve(a.tol)
+        ms, cnt, by = slv.timing(kind)
+        top_ms += ms; top_n += cnt; top_bytes += by
+        ms, cnt, by = slv.timing(0)
+        ttr_ms += ms; ttr_bytes += by
+    inst_ms = maxr(slv.timing(7)[0])
+    top_ms = maxr(top_ms)
+    assert np.array_equal(res_i["relres"], res["relres"]), "graph replay and stream launches disagree"
+    slv.close()
+
+    ttt = e2e = None
+    h2d = d2h = 0
     dl = slv.count
-    # bytes that actually cross PCIe per call: the reference aliases ONE rhs vector and ONE matrix over all d modes
-    # (system.jl:5-11, tensor_struct.jl:208-210) and the library honours that (tk_set_rhs_all, tk_share_operator):
-    # b once, the CSC arrays of A_1 once (colptr, rowval, nzval), the exp-sum schedule (<= 64 terms per iteration)
-    h2d = n * 8 + (n + 1) * 8 + 2 * int(A1.nnz) * 8 + sum(16 * 64 for _ in range(nmax))
-    d2h = 3 * nmax * 8 + 64
+    if not a.no_extras:
+        # ---- time-to-tolerance (second half of BASELINE.json's metric): parity mode, tol 1e-5 -- the only tolerance
+        # this configuration reaches.  The reference's convergent exit builds and returns x
+        # (tensor_krylov_method.jl:108-118), so the honest figure is the public call INCLUDING the solution.
+        if a.d >= 256 and a.n >= 10000 and a.variant == "reorth" and not a.t_override:
+            pm = 0 if a.per_mode else tk.TK_FLAG_REFERENCE_H1
+            s2 = make(pm)
+            feed(s2, 1e-5)
+            best = None
+            for it in range(4):
+                barrier()
+                t0 = time.perf_counter()
+                r2 = s2.solve(1e-5)
+                wall = 1e3 * (time.perf_counter() - t0)
+                dev = maxr(s2.timing(6)[0])
+                if it and (best is None or dev < best[0]):
+                    best = (dev, wall)
+            ttt = {"tol": 1e-5, "status": r2["status"], "iterations": r2["term_k"], "device_ms": best[0], "call_ms": best[1],
+                   "relres": float(r2["relres"][r2["term_k"] - 1]) if r2["term_k"] >= 1 else None,
+                   "solution_rank": s2.solution_rank()}
+            if r2["status"] == tk.TK_CONVERGED:
+                # x to pageable host memory, to pinned host memory, and left on the device
+                t_sol = s2.solution_rank()
+                for mode in ("pageable", "pinned", "device"):
+                    times = []
+                    for it in range(3):
+                        barrier()
+                        t0 = time.perf_counter()
+                        s2.solve(1e-5)
+                        if mode == "device":
+                            xd = torch.empty(max(s2.count, 1) * t_sol * n, dtype=torch.float64, device="cuda")
+                            s2.solution_device(xd.data_ptr(), xd.numel())
+                        else:
+                            s2.solution(pinned=(mode == "pinned"))
+                        times.append(maxr(1e3 * (time.perf_counter() - t0)))
+                    ttt[f"with_solution_ms_{mode}"] = min(times[1:])
+                ttt["solution_bytes_per_gpu"] = s2.count * t_sol * n * 8
+                ttt["with_solution_ms"] = ttt["with_solution_ms_pageable"]
+            s2.close()
+            # the public entry point, fresh handle per call (what a drop-in caller does)
+            A = tk.KroneckerMatrix(instance, [A1] * d, cls)
+            if world == 1:
+                times = []
+                for it in range(3):
+                    cd = tk.ConvergenceData(nmax)
+                    t0 = time.perf_counter()
+                    x = tk.tensorkrylov(cd, A, [b_np] * d, 1e-5, nmax, variant, verbose=False, device=local)
+                    times.append(1e3 * (time.perf_counter() - t0))
+                ttt["public_call_ms"] = min(times[1:])
+                ttt["public_call_returned_x"] = x is not None
+
+        # ---- end-to-end arm: the public path with host buffers, H2D and D2H inside the timed region ------------
+        def e2e_once():
+            cd = tk.ConvergenceData(nmax)
+            s = make(base)
+            try:
+                feed(s)
+                r = s.solve(a.tol)
+                cd.relative_residual_norm[:] = r["relres"]
+            finally:
+                s.close()
+            return cd
+        for _ in range(min(a.warmup, 2)):
+            e2e_once()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            cd = e2e_once()
+        barrier()
+        e2e_ms = maxr(1e3 * (time.perf_counter() - t0))
+        assert abs(cd.relative_residual_norm[nmax - 1] - relres_last) <= 1e-9 * abs(relres_last) + 1e-300
+        # bytes that actually cross PCIe per call: the reference aliases ONE rhs vector and ONE matrix over all d modes
+        # (system.jl:5-11, tensor_struct.jl:208-210) and the library honours that (tk_set_rhs_all, tk_share_operator):
+        # b once, the CSC arrays of A_1 once (colptr, rowval, nzval), the exp-sum schedule (<= 64 terms per iteration)
+        h2d = n * 8 + (n + 1) * 8 + 2 * int(A1.nnz) * 8 + sum(16 * 64 for _ in range(nmax))
+        d2h = 3 * nmax * 8 + 64
+        e2e = {"value": a.steps * (nmax - 1) / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps,
+               "note": "fresh handle per step: handle creation, operator/rhs/schedule upload, solve (stream launches: "
+                       "graphs are only recorded for a handle that solves twice), histories back"}
 
     if rank != 0:
         if world > 1:
@@ -372,33 +488,39 @@ def run_b200(a):
     iters = a.steps * (nmax - 1)
     value = iters / (dev_ms / 1e3)
     peak, peak_kind = measured_peak()
-    achieved = gram_bytes / (gram_ms / 1e3) / 1e9 if gram_ms > 0 else 0.0
-    tr_ratio, tr_src = measured_traffic_ratio()
+    achieved = top_bytes / (top_ms / 1e3) / 1e9 if top_ms > 0 else 0.0
+    tr_ratio, tr_src = measured_traffic_ratio("arnoldi" if kind == 2 else "gram")
+    kname = ("arnoldi_mgs_cluster_kernel (two-pass MGS step of every mode)" if kind == 2
+             else "gram_row_balanced_kernel (orthogonality monitor of the batched Lanczos step)")
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak" if a.weak else "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(a), "iterations_per_step": nmax - 1, "modes_per_gpu": dl,
                    "l2": "inputs larger than L2: the Krylov bases are %.1f GB per GPU, re-streamed every iteration"
                          % (dl * n * (nmax + 1) * 8 / 1e9),
                    "status": status, "relres_last": relres_last, "mgs_fallbacks_mode0": fb,
-                   "wall_ms_per_step": wall_ms / a.steps},
+                   "wall_ms_per_step": wall_ms / a.steps,
+                   "enqueue": {"cuda_graph_launches_per_step": info["graphs_launched"], "segments": info["segments"],
+                               "cross_gpu_exchange": ("peer-mapped stores" if info["peer_exchange"] else "nccl all-gather") if world > 1 else None}},
         "clocks": clocks,
-        "e2e": {"value": iters / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / a.steps,
-                "note": "handle creation (cudaMalloc of the bases), operator/rhs/schedule upload, solve, histories back"},
+        "e2e": e2e,
         "gpu_launches": launches,
         "time_to_tol": ttt,
-        "roofline": {"kernel": "gram_row_kernel (orthogonality monitor of the batched Lanczos step)", "bound": "hbm",
+        "parity": parity,
+        "roofline": {"kernel": kname, "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
-                     "frac_of_nominal_8TBs": achieved / 8000.0, "launches": gram_n,
-                     "algorithmic_bytes_per_launch_avg": gram_bytes / max(gram_n, 1),
-                     "avg_launch_ms": gram_ms / max(gram_n, 1), "share_of_step": gram_ms / dev_ms,
-                     "traffic": (tr_ratio * gram_bytes / max(gram_n, 1)) if (tr_ratio and world == 1) else None,
+                     "frac_of_nominal_8TBs": achieved / 8000.0, "launches": top_n,
+                     "algorithmic_bytes_per_launch_avg": top_bytes / max(top_n, 1),
+                     "avg_launch_ms": top_ms / max(top_n, 1),
+                     "measured_in": "instrumented pass over the same K solves (events around the Krylov-step kernels, stream launches)",
+                     "instrumented_ms_per_step": inst_ms / a.steps, "share_of_step": top_ms / inst_ms,
+                     "traffic": (tr_ratio * top_bytes / max(top_n, 1)) if (tr_ratio and world == 1) else None,
                      "traffic_source": tr_src,
                      "ttr_kernel": {"achieved": (ttr_bytes / (ttr_ms / 1e3) / 1e9) if ttr_ms > 0 else None,
-                                    "share_of_step": ttr_ms / dev_ms}},
+                                    "share_of_step": ttr_ms / inst_ms},
+                     "all_krylov_bytes_over_step": ((top_bytes + ttr_bytes) / a.steps) / (dev_ms / a.steps / 1e3) / 1e9},
     }
     if world == 1 and not a.no_cpu_baseline:
         cb, _ = cpu_arm(a, a.cpu_sample_modes)
@@ -406,6 +528,9 @@ def run_b200(a):
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if parity.get("checked") and not parity.get("ok"):
+        print("PARITY MISS against the oracle fixture: " + json.dumps(parity), file=sys.stderr)
+        return 3
     return 0
 
 

@@ -76,6 +76,9 @@ int tk_tables_load(const char* path);
 /* approximation.jl:65-84 + 119-147: kappa -> (t, omega[t], alpha[t]); omega/alpha need room for 63. */
 int tk_tables_sym_lookup(double kappa, double tol, int32_t* t, int32_t* first_digit, int32_t* order,
                          double* omega, double* alpha);
+/* exponential_sum_parameters! alone (approximation.jl:119-147): the coefficient file of a GIVEN rank in the row kappa
+ * selects, and the tabulated error of that cell; TK_ETABLE if the cell has no file ('--' in the table). */
+int tk_tables_sym_rank(double kappa, int32_t rank, double* omega, double* alpha, double* err);
 /* approximation.jl:86-107 + 150-158: writes 2*rank+1 terms; returns TK_EINVAL if cap is too small. */
 int tk_nonsym_coefficients(double lambda_min, double tol, int32_t cap, int32_t* rank, int32_t* nterms,
                            double* omega, double* alpha);

@@ -25,7 +25,7 @@ TK_FLAG_REFERENCE_H1, TK_FLAG_FIXED_ITERATIONS, TK_FLAG_TIME_KERNELS, TK_FLAG_TI
 
 EXPORTS = [
     "tk_last_error", "tk_version", "tk_device_count",
-    "tk_tables_load", "tk_tables_sym_lookup", "tk_nonsym_coefficients", "tk_laplace_extremes",
+    "tk_tables_load", "tk_tables_sym_lookup", "tk_tables_sym_rank", "tk_nonsym_coefficients", "tk_laplace_extremes",
     "tk_comm_unique_id", "tk_create", "tk_destroy", "tk_release_cache", "tk_local_modes", "tk_needs_mode",
     "tk_set_operator_csc", "tk_set_operator_dense", "tk_share_operator", "tk_share_operator_all", "tk_set_rhs", "tk_set_rhs_all",
     "tk_set_schedule", "tk_schedule_laplace", "tk_solve", "tk_solution_rank", "tk_get_solution", "tk_get_solution_all",
@@ -57,6 +57,7 @@ def _load():
         "tk_device_count": (C.c_int, [C.POINTER(C.c_int)]),
         "tk_tables_load": (C.c_int, [C.c_char_p]),
         "tk_tables_sym_lookup": (C.c_int, [f64, f64, pi32, pi32, pi32, pd, pd]),
+        "tk_tables_sym_rank": (C.c_int, [f64, i32, pd, pd, pd]),
         "tk_nonsym_coefficients": (C.c_int, [f64, f64, i32, pi32, pi32, pd, pd]),
         "tk_laplace_extremes": (C.c_int, [i32, i64, i32, pd, pd]),
         "tk_comm_unique_id": (C.c_int, [p]),

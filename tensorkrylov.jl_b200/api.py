@@ -179,6 +179,14 @@ def sym_lookup(kappa, tol):
     return t.value, om[:t.value].copy(), al[:t.value].copy(), dg.value, od.value
 
 
+def sym_rank_coefficients(kappa, rank):
+    """The coefficient file of a given rank in kappa's table row (approximation.jl:119-147): (omega, alpha, error)."""
+    _capi.load_tables()
+    om, al, err = np.zeros(64), np.zeros(64), C.c_double()
+    check(lib.tk_tables_sym_rank(kappa, rank, dptr(om), dptr(al), C.byref(err)))
+    return om[:rank].copy(), al[:rank].copy(), err.value
+
+
 def nonsym_coefficients(lambda_min, tol):
     """approximation.jl:86-107, 150-158"""
     cap = 8192

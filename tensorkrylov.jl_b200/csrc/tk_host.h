@@ -8,6 +8,7 @@ namespace tk {
 int set_error(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
 
 int tables_sym_lookup(double kappa, double tol, int* t, int* digit, int* order, const double** omega, const double** alpha);
+int tables_sym_rank(double kappa, int rank, const double** omega, const double** alpha, double* err);
 void laplace_extremes(int d, long long n, int k, double* lmin, double* lmax);
 int nonsym_coefficients(double lambda_min, double tol, std::vector<double>& omega, std::vector<double>& alpha, int* rank);
 

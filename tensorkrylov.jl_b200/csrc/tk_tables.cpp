@@ -154,6 +154,34 @@ int tables_sym_lookup(double kappa, double tol, int* t_out, int* digit_out, int*
     return 0;
 }
 
+// exponential_sum_parameters! on its own (approximation.jl:119-147): the coefficient file of a GIVEN rank in the
+// row the condition number selects, with the tabulated error of that cell.
+int tables_sym_rank(double kappa, int rank, const double** omega, const double** alpha, double* err) {
+    if (!g_tables.loaded) return set_error(TK_ETABLE, "exponential-sum tables not loaded (tk_tables_load)");
+    if (!(kappa >= 1.0) || !std::isfinite(kappa)) return set_error(TK_EINVAL, "condition number %g is not a finite value >= 1", kappa);
+    int order = (int)std::floor(std::log10(kappa));
+    int digit = (int)std::floor(kappa / std::pow(10.0, (double)order));
+    int row = -1;
+    for (int guard = 0; guard < 1000 && row < 0; ++guard) {
+        const double want = digit * std::pow(10.0, (double)order);
+        for (size_t r = 0; r < g_tables.R.size(); ++r)
+            if (g_tables.R[r] == want) { row = (int)r; break; }
+        if (row < 0) digit += 1;
+    }
+    if (row < 0) return set_error(TK_ETABLE, "condition number %g is outside the table", kappa);
+    auto it = g_tables.coeffs.find(std::make_tuple(rank, digit, order));
+    if (it == g_tables.coeffs.end()) return set_error(TK_ETABLE, "no coefficient file 1_xk%02d.%d_%d", rank, digit, order);
+    const size_t nr = g_tables.ranks.size();
+    if (err) {
+        *err = INFINITY;
+        for (size_t c = 0; c < nr; ++c)
+            if (g_tables.ranks[c] == rank) *err = g_tables.err[(size_t)row * nr + c];
+    }
+    *omega = it->second.first.data();
+    *alpha = it->second.second.data();
+    return 0;
+}
+
 void laplace_extremes(int d, long long n, int k, double* lmin, double* lmax) {
     // laplace_eigenvalue / analytic_eigenvalues, eigenvalues.jl:247-265
     const double h = 1.0 / (double)(n + 1);
@@ -202,6 +230,15 @@ int tk_tables_sym_lookup(double kappa, double tol, int32_t* t, int32_t* first_di
     if (order) *order = od;
     if (omega) std::memcpy(omega, om, 8 * (size_t)tt);
     if (alpha) std::memcpy(alpha, al, 8 * (size_t)tt);
+    return 0;
+}
+
+int tk_tables_sym_rank(double kappa, int32_t rank, double* omega, double* alpha, double* err) {
+    const double *om, *al;
+    int rc = tk::tables_sym_rank(kappa, rank, &om, &al, err);
+    if (rc) return rc;
+    if (omega) std::memcpy(omega, om, 8 * (size_t)rank);
+    if (alpha) std::memcpy(alpha, al, 8 * (size_t)rank);
     return 0;
 }
 
