@@ -192,7 +192,8 @@ def measured_peak():
 # ---------------------------------------------------------------------------------------------
 def parity_check(a, detail, relres):
     """Iterations 2..16 of the benchmarked solve against tests/golden/c{3,5}_oracle.npz (tolerance model of
-    SURVEY.md 8c: terms 1e-11 relative, boundary 1e-10, r_comp 1e-11 of the terms it cancels, relres^2 4e-11)."""
+    SURVEY.md 8c: terms 1e-11 relative, r_comp and the boundary term 1e-11 of the terms r_comp cancels (the boundary
+    term also 1e-10 relative while it is above rounding level), relres^2 4e-11)."""
     name = {(256, 10000): "c3", (1024, 10000): "c5"}.get((a.d, a.n))
     if (name is None or a.cls != "Laplace" or a.variant != "reorth" or a.per_mode or a.t_override or a.tol != 1e-8
             or a.nmax < 16):
@@ -201,13 +202,19 @@ def parity_check(a, detail, relres):
     ks = ref["k"]
     m = len(ks)
     worst = {}
-    for key in ("hy2", "hyb", "bb", "boundary"):
+    for key in ("hy2", "hyb", "bb"):
         worst[key] = float((np.abs(detail[key][:m] - ref[key]) / np.abs(ref[key])).max())
     scale = np.abs(ref["hy2"]) + 2 * np.abs(ref["hyb"]) + np.abs(ref["bb"])
+    # the boundary term decays to rounding level of the last rows of Y within a few iterations: relative where it
+    # matters, else on the scale it enters relres^2 = (boundary + r_comp)/||b||^2 with (the absolute bound of r_comp)
+    db = np.abs(detail["boundary"][:m] - ref["boundary"])
+    worst["boundary"] = float(np.minimum(db / np.abs(ref["boundary"]) / 10.0, db / scale).max())
+    big = ref["boundary"] > 1e-9 * scale
+    worst["boundary_rel_k2_5"] = float((db / np.abs(ref["boundary"]))[big].max()) if big.any() else 0.0
     worst["r_comp_over_terms"] = float((np.abs(detail["r_comp"][:m] - ref["r_comp"]) / scale).max())
     worst["relres_sq_abs"] = float(np.abs(relres[ks - 1] ** 2 - ref["relres"][ks - 1] ** 2).max())
-    ok = (max(worst["hy2"], worst["hyb"], worst["bb"], worst["r_comp_over_terms"]) < 1e-11 and worst["boundary"] < 1e-10
-          and worst["relres_sq_abs"] < 4e-11 and np.array_equal(detail["t"][:m].astype(int), ref["t"]))
+    ok = (max(worst["hy2"], worst["hyb"], worst["bb"], worst["r_comp_over_terms"], worst["boundary"]) < 1e-11
+          and worst["boundary_rel_k2_5"] < 1e-10 and worst["relres_sq_abs"] < 4e-11 and np.array_equal(detail["t"][:m].astype(int), ref["t"]))
     return {"checked": True, "ok": bool(ok), "fixture": f"tests/golden/{name}_oracle.npz", "iterations": [int(ks[0]), int(ks[-1])],
             "worst": worst, "relres_k16": float(relres[15]), "relres_k16_oracle": float(ref["relres"][15])}
 

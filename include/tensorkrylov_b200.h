@@ -127,6 +127,14 @@ int tk_set_rhs_all(tk_handle* h, const double* b, int64_t n);
 int tk_set_schedule(tk_handle* h, int32_t k, double lambda_min, int32_t t, const double* alpha, const double* omega);
 /* fills k = 2..nmax for Laplace / SymInstance from the loaded tables (eigenvalues.jl:335 + approximation.jl:160-168) */
 int tk_schedule_laplace(tk_handle* h, double tol);
+/* the same for every (instance, matrix class) the reference has an extreme_eigvals method for (eigenvalues.jl:335-350):
+ * Laplace analytic; RandSPD, and every NonSymInstance class, from the eigenvalues of the leading k x k minors of the
+ * operator fed for mode 0 (computed here on the host threads, cached per operator); EigValMat from its diagonal.
+ * Needs the tables (Sym) and mode 0's operator on THIS rank (feed mode 0 to every rank; it is ignored otherwise). */
+int tk_schedule(tk_handle* h, double tol);
+/* the spectral kernel of tk_schedule on its own: (min, max) eigenvalue of the leading k x k minors, k = 1..nmax, of a
+ * column-major ld x ld block; out[2k], out[2k+1] (out holds 2*(nmax+1) doubles; general != 0: minimum only, max = NaN) */
+int tk_minor_extremes(const double* lead, int32_t ld, int32_t nmax, int32_t general, double* out);
 
 /* ---- the solve: tensorkrylov! (tensor_krylov_method.jl:36-125).
  * relres/projres/orth: nmax doubles each, written like ConvergenceData

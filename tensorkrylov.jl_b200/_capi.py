@@ -28,7 +28,7 @@ EXPORTS = [
     "tk_tables_load", "tk_tables_sym_lookup", "tk_tables_sym_rank", "tk_nonsym_coefficients", "tk_laplace_extremes",
     "tk_comm_unique_id", "tk_create", "tk_destroy", "tk_release_cache", "tk_local_modes", "tk_needs_mode",
     "tk_set_operator_csc", "tk_set_operator_dense", "tk_share_operator", "tk_share_operator_all", "tk_set_rhs", "tk_set_rhs_all",
-    "tk_set_schedule", "tk_schedule_laplace", "tk_solve", "tk_solution_rank", "tk_get_solution", "tk_get_solution_all",
+    "tk_set_schedule", "tk_schedule_laplace", "tk_schedule", "tk_minor_extremes", "tk_solve", "tk_solution_rank", "tk_get_solution", "tk_get_solution_all",
     "tk_get_solution_device", "tk_alloc_host", "tk_free_host", "tk_get_detail", "tk_get_solve_info",
     "tk_begin", "tk_step_bases", "tk_compress", "tk_residual",
     "tk_get_H", "tk_get_V", "tk_get_bt", "tk_get_Y", "tk_get_eig", "tk_get_orth_state",
@@ -74,6 +74,8 @@ def _load():
         "tk_set_rhs_all": (C.c_int, [p, pd, i64]),
         "tk_set_schedule": (C.c_int, [p, i32, f64, i32, pd, pd]),
         "tk_schedule_laplace": (C.c_int, [p, f64]),
+        "tk_schedule": (C.c_int, [p, f64]),
+        "tk_minor_extremes": (C.c_int, [pd, i32, i32, i32, pd]),
         "tk_solve": (C.c_int, [p, f64, pi32, pi64, pi32, pd, pd, pd]),
         "tk_solution_rank": (C.c_int, [p, pi32]),
         "tk_get_solution": (C.c_int, [p, i32, pd, i32, pd, i64, i32]),

@@ -196,6 +196,10 @@ def nonsym_coefficients(lambda_min, tol):
     return rank.value, om[:nt.value].copy(), al[:nt.value].copy()
 
 
+# where Solver.set_schedule takes the eigen-extremes of the minors of A_1 from: "library" (tk_schedule) or "lapack"
+DEFAULT_SPECTRAL = "library"
+
+
 # ---- the device-resident solver --------------------------------------------------------------
 class Solver:
     """One tk_handle: the state tensorkrylov! keeps in `tensor_decomp`, b~, spectraldata, approxdata."""
@@ -243,18 +247,7 @@ class Solver:
             if id(A) in seen:
                 check(lib.tk_share_operator(self.h, s, seen[id(A)]))
                 continue
-            if sp.issparse(A):
-                Ac = A.tocsc()
-                Ac.sort_indices()
-                colptr = np.ascontiguousarray(Ac.indptr, dtype=np.int64) + 1      # Julia is 1-based
-                rowval = np.ascontiguousarray(Ac.indices, dtype=np.int64) + 1
-                nz = np.ascontiguousarray(Ac.data, dtype=np.float64)
-                check(lib.tk_set_operator_csc(self.h, s, Ac.shape[0],
-                                              colptr.ctypes.data_as(C.POINTER(C.c_int64)),
-                                              rowval.ctypes.data_as(C.POINTER(C.c_int64)), dptr(nz)))
-            else:
-                Af = np.asfortranarray(A, dtype=np.float64)
-                check(lib.tk_set_operator_dense(self.h, s, Af.shape[0], dptr(Af), b"F"))
+            self._feed_operator(s, A)
             seen[id(A)] = s
 
     def set_rhs(self, b):
@@ -267,11 +260,36 @@ class Solver:
             v = _capi.as_f64(b[s])
             check(lib.tk_set_rhs(self.h, s, dptr(v), len(v)))
 
-    def set_schedule(self, A1, tol):
-        """The two update_data! calls of every iteration (tensor_krylov_method.jl:72-73), hoisted."""
+    def _feed_operator(self, s, A):
+        if sp.issparse(A):
+            Ac = A.tocsc()
+            Ac.sort_indices()
+            colptr = np.ascontiguousarray(Ac.indptr, dtype=np.int64) + 1      # Julia is 1-based
+            rowval = np.ascontiguousarray(Ac.indices, dtype=np.int64) + 1
+            nz = np.ascontiguousarray(Ac.data, dtype=np.float64)
+            check(lib.tk_set_operator_csc(self.h, s, Ac.shape[0],
+                                          colptr.ctypes.data_as(C.POINTER(C.c_int64)),
+                                          rowval.ctypes.data_as(C.POINTER(C.c_int64)), dptr(nz)))
+        else:
+            Af = np.asfortranarray(A, dtype=np.float64)
+            check(lib.tk_set_operator_dense(self.h, s, Af.shape[0], dptr(Af), b"F"))
+
+    def set_schedule(self, A1, tol, spectral=None):
+        """The two update_data! calls of every iteration (tensor_krylov_method.jl:72-73), hoisted out of the loop.
+
+        spectral="library" (default): tk_schedule -- the eigen-extremes of the leading minors of A_1
+        (eigenvalues.jl:335-350) are computed inside the library on the host threads.  spectral="lapack": they come
+        from numpy's LAPACK here (`extreme_eigvals`) and are fed through tk_set_schedule, the way the Julia wrapper
+        feeds Julia's own SpectralData; the two agree to eps * cond(minor) in lambda_min."""
         _capi.load_tables()
+        spectral = spectral or DEFAULT_SPECTRAL
         if self.instance is SymInstance and self.matrixclass is Laplace:
             check(lib.tk_schedule_laplace(self.h, tol))
+            return
+        if spectral == "library":
+            if 0 not in self.fed:
+                self._feed_operator(0, A1)       # only its leading block is kept on a rank that does not own mode 1
+            check(lib.tk_schedule(self.h, tol))
             return
         for k in range(2, self.nmax + 1):
             lmin, lmax = extreme_eigvals(A1, self.d, k, self.instance, self.matrixclass)

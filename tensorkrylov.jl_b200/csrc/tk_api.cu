@@ -21,6 +21,7 @@
 #include <mutex>
 #include <set>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/tensorkrylov_b200.h"
@@ -221,6 +222,8 @@ struct tk_resources {
     std::vector<cudaEvent_t> ev_pool;   // timing events, grown on demand
 };
 static std::vector<tk_resources*> g_res_free;
+static std::map<size_t, std::vector<void*>> g_host_pool;   // parked page-locked blocks of tk_alloc_host, by size
+static std::map<void*, size_t> g_host_live;
 
 static int acquire_resources(int device, tk_resources** out) {
     {
@@ -328,6 +331,7 @@ struct tk_handle {
     std::vector<int> mode_op;   // local mode -> op index (-1 unset)
     std::vector<char> rhs_set;
     bool ops_dirty = true;
+    std::vector<double> a1_lead;   // leading nmax x nmax block of global mode 0's operator (spectral data, eigenvalues.jl:276-282)
 
     // schedule
     std::vector<SchedEntry> sched;
@@ -778,6 +782,21 @@ static int launch_arnoldi(tk_handle* h, int k) {
         TK_CUDA(cudaGetLastError());                                                  \
         return 0;                                                                     \
     } while (0)
+    // blocked sweep (4 columns per reduction round) where the registers allow it; TK_MGS_BLOCK=0 keeps strict MGS
+#define TK_BGS_LAUNCH(E, TH, BB)                                                      \
+    do {                                                                              \
+        arnoldi_bgs_kernel<E, TH, BB><<<h->dk, TH, hsm, h->stream>>>(p, k);           \
+        h->launches++;                                                                \
+        TK_CUDA(cudaGetLastError());                                                  \
+        return 0;                                                                     \
+    } while (0)
+    if (reg_ok && hsm <= 40 * 1024 && env_int("TK_MGS_BLOCK", 1)) {
+        if (h->n <= 128 * 4) TK_BGS_LAUNCH(4, 128, 4);
+        if (h->n <= 256 * 4) TK_BGS_LAUNCH(4, 256, 4);
+        if (h->n <= 256 * 8) TK_BGS_LAUNCH(8, 256, 4);
+        if (h->n <= 512 * 8) TK_BGS_LAUNCH(8, 512, 2);     // 128 registers per thread at 512 threads: two columns per round
+    }
+#undef TK_BGS_LAUNCH
     if (reg_ok && hsm <= 40 * 1024) {
         if (h->n <= 128 * 4) TK_MGS_LAUNCH(4, 128, 3);
         if (h->n <= 256 * 4) TK_MGS_LAUNCH(4, 256, 3);
@@ -1242,8 +1261,10 @@ static int enqueue_segment(tk_handle* h, int idx) {
 static void plan_segments(tk_handle* h) {
     if (!h->segs.empty()) return;
     // short segments first (a solve that ends after a few iterations has little enqueued behind its exit), then 16
-    const int cap = std::max(1, env_int("TK_SEG", 16)), lag = std::max(0, env_int("TK_SEG_LAG", 3));
+    // chains deferred across a boundary: 3 in fixed-iteration runs (no exit to detect; the Krylov stream never waits
+    // for a chain), 1 otherwise (an exit is seen at most one chain later; the bubble at a boundary stays under one step)
     const bool fixed = (h->flags & TK_FLAG_FIXED_ITERATIONS) != 0;
+    const int cap = std::max(1, env_int("TK_SEG", 16)), lag = std::max(0, env_int("TK_SEG_LAG", fixed ? 3 : 1));
     int k = 2, size = fixed ? cap : std::min(cap, 4), count = 0, prev_c1 = 1;
     do {
         tk_handle::Segment sg;
@@ -1460,6 +1481,9 @@ int tk_release_cache(void) {
         delete r;
     }
     g_res_free.clear();
+    for (auto& kv : g_host_pool)
+        for (void* q : kv.second) cudaFreeHost(q);
+    g_host_pool.clear();
     pool_trim();
     return 0;
 }
@@ -1476,11 +1500,20 @@ int tk_set_operator_csc(tk_handle* h, int32_t s, int64_t n, const int64_t* colpt
     TK_TRY(check_mode(h, s, &local));
     if (n != h->n) return set_error(TK_EINVAL, "operator order %lld != n = %d (system.jl:27-28)", (long long)n, h->n);
     if (!colptr || !rowval || !nzval) return set_error(TK_EINVAL, "null CSC array");
+    if (colptr[0] != 1) return set_error(TK_EINVAL, "colptr must be 1-based (Julia SparseMatrixCSC)");
+    if (s == 0) {        // every rank keeps the leading block of A_1: the exp-sum schedule is derived from its minors
+        const int m = h->nmax;
+        h->a1_lead.assign((size_t)m * m, 0.0);
+        for (int64_t j = 0; j < m; ++j)
+            for (int64_t p = colptr[j] - 1; p < colptr[j + 1] - 1; ++p) {
+                const int64_t i = rowval[p] - 1;
+                if (i >= 0 && i < m) h->a1_lead[(size_t)j * m + i] += nzval[p];
+            }
+    }
     int slots[2];
     const int nslots = slots_of(h, s, slots);
     if (nslots == 0) return 0;
     TK_CUDA(cudaSetDevice(h->device));
-    if (colptr[0] != 1) return set_error(TK_EINVAL, "colptr must be 1-based (Julia SparseMatrixCSC)");
     const int64_t nnz = colptr[n] - 1;
     std::set<long long> offs;
     for (int64_t j = 0; j < n; ++j) {
@@ -1558,6 +1591,13 @@ int tk_set_operator_dense(tk_handle* h, int32_t s, int64_t n, const double* a, c
     if (n != h->n) return set_error(TK_EINVAL, "operator order %lld != n = %d", (long long)n, h->n);
     if (!a) return set_error(TK_EINVAL, "null matrix");
     if (uplo != 'L' && uplo != 'F') return set_error(TK_EINVAL, "uplo must be 'L' or 'F'");
+    if (s == 0) {
+        const int m = h->nmax;
+        h->a1_lead.assign((size_t)m * m, 0.0);
+        for (int j = 0; j < m; ++j)
+            for (int i = 0; i < m; ++i)
+                h->a1_lead[(size_t)j * m + i] = (uplo == 'L' && i < j) ? a[(size_t)i * n + j] : a[(size_t)j * n + i];
+    }
     int slots[2];
     const int nslots = slots_of(h, s, slots);
     if (nslots == 0) return 0;
@@ -1695,6 +1735,46 @@ int tk_schedule_laplace(tk_handle* h, double tol) {
         const double *om, *al;
         TK_TRY(tables_sym_lookup(kappa, tol, &t, &dg, &od, &om, &al));
         TK_TRY(tk_set_schedule(h, k, lmin, t, al, om));
+    }
+    return 0;
+}
+
+int tk_schedule(tk_handle* h, double tol) {
+    if (!h) return set_error(TK_EINVAL, "null handle");
+    if (h->instance == TK_SYM && h->matrixclass == TK_LAPLACE) return tk_schedule_laplace(h, tol);
+    if (h->a1_lead.empty())
+        return set_error(TK_ESTATE, "operator of mode 0 not set on this rank: its leading minors define the spectral data (eigenvalues.jl:276-282); feed mode 0 to every rank");
+    const int m = h->nmax;
+    std::vector<double> ext(2 * (size_t)(m + 1), 0.0);
+    if (h->instance == TK_NONSYM) {
+        TK_TRY(minor_extremes(h->a1_lead, m, m, 1, ext));                   // eigenvalues.jl:344-350
+    } else if (h->matrixclass == TK_RANDSPD) {
+        TK_TRY(minor_extremes(h->a1_lead, m, m, 0, ext));                   // eigenvalues.jl:337
+    } else if (h->matrixclass == TK_EIGVALMAT) {
+        double lo = INFINITY, hi = -INFINITY;                               // eigenvalues.jl:339
+        for (int k = 1; k <= m; ++k) {
+            const double dg = h->a1_lead[(size_t)(k - 1) * m + (k - 1)];
+            lo = std::min(lo, dg); hi = std::max(hi, dg);
+            ext[2 * k] = lo; ext[2 * k + 1] = hi;
+        }
+    } else {
+        return set_error(TK_EUNSUPPORTED, "the reference has no extreme_eigvals method for SymInstance with matrix class %d (eigenvalues.jl:335-350)", h->matrixclass);
+    }
+    std::vector<double> om, al;
+    for (int k = 2; k <= m; ++k) {
+        const double lmin = ext[2 * k] * (double)h->d;
+        if (h->instance == TK_NONSYM) {
+            int rank = 0;
+            TK_TRY(nonsym_coefficients(lmin, tol, om, al, &rank));
+            TK_TRY(tk_set_schedule(h, k, lmin, (int)om.size(), al.data(), om.data()));
+        } else {
+            const double lmax = ext[2 * k + 1] * (double)h->d;
+            const double kappa = lmax * (1.0 / lmin);                       // eigenvalues.jl:360
+            int t, dg, od;
+            const double *o, *a;
+            TK_TRY(tables_sym_lookup(kappa, tol, &t, &dg, &od, &o, &a));
+            TK_TRY(tk_set_schedule(h, k, lmin, t, a, o));
+        }
     }
     return 0;
 }
@@ -1877,7 +1957,19 @@ static int solution_to_host(tk_handle* h, int k, int t, int tld, int m0, int nm,
     auto drain = [&](int c) -> int {           // pageable destination: staging buffer of chunk c -> caller's memory
         const int c0 = c * cm, cn = std::min(cm, nm - c0);
         TK_CUDA(cudaEventSynchronize(r->copy_ev[c & 1]));
-        std::memcpy(fmat + (size_t)c0 * per_mode, r->stage[c & 1], (size_t)cn * per_mode * 8);
+        // a fresh destination is first touched here (page faults): several host threads share the copy
+        const size_t bytes = (size_t)cn * per_mode * 8;
+        char* dst = reinterpret_cast<char*>(fmat + (size_t)c0 * per_mode);
+        const char* src = reinterpret_cast<const char*>(r->stage[c & 1]);
+        const int nthr = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(8, std::thread::hardware_concurrency()), bytes >> 20));
+        std::vector<std::thread> pool;
+        const size_t piece = ((bytes / nthr) + 4095) & ~(size_t)4095;
+        for (int i = 1; i < nthr; ++i) {
+            const size_t o = (size_t)i * piece;
+            if (o < bytes) pool.emplace_back([=]() { std::memcpy(dst + o, src + o, std::min(piece, bytes - o)); });
+        }
+        std::memcpy(dst, src, std::min(piece, bytes));
+        for (auto& th : pool) th.join();
         return 0;
     };
     for (int c = 0; c < nch; ++c) {
@@ -1956,14 +2048,34 @@ int tk_get_solution_device(tk_handle* h, double* lambda, int32_t lambda_cap, dou
     return 0;
 }
 
+// Page-locking memory costs ~0.3 ms per MB, far more than moving it: freed blocks are parked (by size) for the next
+// request of the same size; tk_release_cache returns them to the system.
 int tk_alloc_host(void** out, int64_t bytes) {
     if (!out || bytes < 0) return set_error(TK_EINVAL, "bad arguments");
-    TK_CUDA(cudaMallocHost(out, (size_t)std::max<int64_t>(bytes, 1)));
+    const size_t sz = (size_t)std::max<int64_t>(bytes, 1);
+    {
+        std::lock_guard<std::mutex> lock(g_mutex);
+        auto it = g_host_pool.find(sz);
+        if (it != g_host_pool.end() && !it->second.empty()) {
+            *out = it->second.back();
+            it->second.pop_back();
+            g_host_live[*out] = sz;
+            return 0;
+        }
+    }
+    TK_CUDA(cudaMallocHost(out, sz));
+    std::lock_guard<std::mutex> lock(g_mutex);
+    g_host_live[*out] = sz;
     return 0;
 }
 
 int tk_free_host(void* p) {
-    if (p) TK_CUDA(cudaFreeHost(p));
+    if (!p) return 0;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    auto it = g_host_live.find(p);
+    if (it == g_host_live.end()) return set_error(TK_EINVAL, "pointer was not returned by tk_alloc_host");
+    g_host_pool[it->second].push_back(p);
+    g_host_live.erase(it);
     return 0;
 }
 

@@ -730,6 +730,124 @@ __global__ void __launch_bounds__(THREADS) arnoldi_mgs_reg_kernel(KrylovParams p
 }
 
 // ------------------------------------------------------------------------------------------
+// Blocked form of the Arnoldi step.  Strict MGS is a chain of 2k dependent CTA-wide reductions (~0.35 us each on
+// B200: two shuffle trees, a barrier and the dependent FP64 adds), which bounds arnoldi_mgs_reg_kernel at ~0.3 of
+// the HBM roofline however fast the columns arrive.  Here the basis columns are taken B at a time: the B projections
+// of a block are computed against the SAME working vector in one reduction round (classical Gram-Schmidt inside the
+// block), then subtracted in column order; blocks follow each other as in MGS, and the whole sweep runs twice like
+// the reference's (orthogonal_bases.jl:22-33).  Against strict MGS the projection on column i of a block differs by
+// sum_{j<i in block} h_j (v_j . v_i): the basis of TensorArnoldi has gone through two passes at every step, so
+// v_j . v_i = O(eps) and the difference is O(eps ||A||) per entry of H -- rounding level, far inside the 1e-11 parity
+// bound (tests/test_gpu_parity.py::test_arnoldi_steps, test_gpu_baseline_sizes.py C4).  The MGS fallback of
+// TensorLanczosReorth, whose basis HAS lost orthogonality when it fires, keeps the strict order (mgs_step_cta).
+// The chain is 2k/B reductions, the next block is in flight while the current one is reduced: HBM-bound.
+// ------------------------------------------------------------------------------------------
+template <int EPT, int THREADS, int B>
+__global__ void __launch_bounds__(THREADS) arnoldi_bgs_kernel(KrylovParams p, int k) {
+    if (!cta_running(p.status)) return;
+    extern __shared__ double hcol[];                    // k+1
+    __shared__ double scr[2][B][32];
+    const int s = blockIdx.x, n = p.n, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = THREADS / 32;
+    const OpDesc& op = p.ops[p.mode_op[s]];
+    double* Vs = p.V + (long long)s * p.vstride;
+    const double* vk = Vs + (long long)(k - 1) * p.ldv;
+    double v[EPT], ca[B][EPT], cb[B][EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int i = tid + e * THREADS;
+        v[e] = (i < n) ? apply_row(op, vk, i, n) : 0.0;
+    }
+    int buf = 0;
+    auto load_block = [&](double (&dst)[B][EPT], int c0) {
+#pragma unroll
+        for (int q = 0; q < B; ++q) {
+            const double* col = Vs + (long long)min(c0 + q, k - 1) * p.ldv;
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) { const int i = tid + e * THREADS; dst[q][e] = (i < n) ? col[i] : 0.0; }
+        }
+    };
+    auto process = [&](double (&blk)[B][EPT], int c0, int pass) {
+        const int nb = min(B, k - c0);                  // uniform across the CTA
+        double h[B];
+#pragma unroll
+        for (int q = 0; q < B; ++q) {
+            double a0 = 0.0, a1 = 0.0;                  // two chains per column: halves the dependent-FMA latency
+#pragma unroll
+            for (int e = 0; e < EPT; e += 2) {
+                a0 = fma(v[e], blk[q][e], a0);
+                if (e + 1 < EPT) a1 = fma(v[e + 1], blk[q][e + 1], a1);
+            }
+            h[q] = warp_sum(a0 + a1);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < B; ++q) scr[buf][q][warp] = h[q];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < B; ++q) h[q] = warp_sum((lane < NW) ? scr[buf][q][lane] : 0.0);
+        buf ^= 1;
+#pragma unroll
+        for (int q = 0; q < B; ++q) {
+            if (q < nb) {
+                if (tid == 0) hcol[c0 + q] = pass ? hcol[c0 + q] + h[q] : h[q];
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) v[e] = fma(-h[q], blk[q][e], v[e]);
+            }
+        }
+    };
+    for (int pass = 0; pass < 2; ++pass) {
+        load_block(ca, 0);
+        for (int c0 = 0; c0 < k; c0 += 2 * B) {
+            if (c0 + B < k) load_block(cb, c0 + B);
+            process(ca, c0, pass);
+            if (c0 + B < k) {
+                if (c0 + 2 * B < k) load_block(ca, c0 + 2 * B);
+                process(cb, c0 + B, pass);
+            }
+        }
+    }
+    auto reduce1 = [&](double x) -> double {
+        x = warp_sum(x);
+        if (lane == 0) scr[buf][0][warp] = x;
+        __syncthreads();
+        const double r = (lane < NW) ? scr[buf][0][lane] : 0.0;
+        buf ^= 1;
+        return warp_sum(r);
+    };
+    double acc = 0.0;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) acc = fma(v[e], v[e], acc);
+    const double beta = sqrt(reduce1(acc));
+    const double inv = 1.0 / beta;                      // no zero-norm guard in the reference (:35-36)
+    double* vnew = Vs + (long long)k * p.ldv;
+    const double* b = p.b + (long long)s * p.ldv;
+    acc = 0.0;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const int i = tid + e * THREADS;
+        if (i < n) {
+            const double x = v[e] * inv;
+            vnew[i] = x;
+            acc = fma(x, b[i], acc);
+        }
+    }
+    const double btn = reduce1(acc);
+    __syncthreads();
+    double* Hs = p.Hd + (long long)s * p.ncol * p.ncol + (long long)(k - 1) * p.ncol;
+    for (int c = tid; c < k; c += THREADS) Hs[c] = hcol[c];
+    if (tid == 0) {
+        Hs[k] = beta;
+        p.bt[(long long)s * p.ncol + k] = btn;
+        double* T = p.T + (long long)s * 3 * p.ncol;
+        T[k - 1] = hcol[k - 1];
+        T[p.ncol + (k - 1)] = beta;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Arnoldi step k for every mode: one CTA per mode runs the two-pass MGS and stores column k of
 // the Hessenberg matrix.  Algorithmic HBM bytes per mode: (16 k + 8 (ndiag + 3)) n.
 // ------------------------------------------------------------------------------------------

@@ -26,7 +26,12 @@ def tk():
     """The product package (ctypes over libtensorkrylov_b200.so); builds the library if it is missing."""
     if not os.path.exists(os.path.join(entry.PKG_DIR, "libtensorkrylov_b200.so")):
         entry.build()
-    return entry.load_package()
+    pkg = entry.load_package()
+    # Parity tests compare with the oracle, whose spectral data (minors of A_1) comes from LAPACK like the reference's:
+    # feed the same numbers (what the Julia wrapper does with Julia's own SpectralData).  The library's own
+    # eigen-extremes (tk_schedule) differ from LAPACK's by eps * cond(minor) and have their own tests.
+    pkg.api.DEFAULT_SPECTRAL = "lapack"
+    return pkg
 
 
 @pytest.fixture(scope="session")

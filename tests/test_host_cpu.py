@@ -303,3 +303,51 @@ def test_device_code_is_the_measured_device_code(tk):
     rec = dict(reversed(l.split("  ", 1)) for l in open(sf.REC).read().splitlines() if l.strip())
     changed = sorted(k for k in set(fp) | set(rec) if fp.get(k) != rec.get(k))
     assert not changed, f"device code differs from profiles/sass_fingerprint.txt for {len(changed)} kernels, e.g. {changed[:3]}"
+
+
+def test_minor_extremes_match_lapack(tk):
+    """f1: the eigen-extremes of the leading minors of A_1 (eigenvalues.jl:335-350) computed inside the library
+    (tk_minor_extremes: Householder + Sturm bisection / Hessenberg QR on the host threads) against LAPACK, for the
+    classes the reference has a method for.  Two backward-stable algorithms agree to a few eps * ||minor||."""
+    import scipy.sparse as sp
+    capi, lib = tk._capi, tk._capi.lib
+    eps = np.finfo(float).eps
+
+    def ext(A, nmax, general):
+        lead = np.asfortranarray(A[:nmax, :nmax].toarray() if sp.issparse(A) else np.asarray(A)[:nmax, :nmax], dtype=float)
+        out = np.zeros(2 * (nmax + 1))
+        assert lib.tk_minor_extremes(capi.dptr(lead), nmax, nmax, general, capi.dptr(out)) == 0, lib.tk_last_error()
+        return out.reshape(-1, 2), lead
+
+    # NonSymInstance / ConvDiff: minimum(eigvals(A_1[1:k,1:k])), an already-Hessenberg banded operator
+    o, lead = ext(tk.assemble_matrix(300, tk.ConvDiff), 80, 1)
+    for k in (2, 3, 17, 80):
+        ev = np.linalg.eigvals(lead[:k, :k])
+        assert abs(o[k, 0] - ev.real.min()) <= 200 * eps * np.abs(lead[:k, :k]).sum(axis=0).max()
+        assert np.isnan(o[k, 1])
+    # a dense non-symmetric matrix whose minors have real spectra (D S D^-1, S symmetric): needs the Hessenberg reduction
+    rng = np.random.default_rng(0)
+    X = rng.normal(size=(40, 40))
+    Dg = np.exp(rng.normal(size=40))
+    M = (X @ X.T + 40 * np.eye(40)) * Dg[:, None] / Dg[None, :]
+    o, lead = ext(M, 30, 1)
+    for k in (2, 5, 12, 30):
+        ev = np.linalg.eigvals(lead[:k, :k])
+        assert np.abs(ev.imag).max() == 0
+        assert abs(o[k, 0] - ev.real.min()) <= 1e-12 * np.abs(ev).max()
+    # SymInstance / RandSPD: both extremes of a dense symmetric minor
+    S = tk.assemble_matrix(60, tk.RandSPD, rng=np.random.default_rng(3))
+    o, lead = ext(S, 59, 0)
+    for k in (2, 3, 30, 59):
+        ev = np.linalg.eigvalsh(lead[:k, :k])
+        assert abs(o[k, 0] - ev[0]) <= 100 * eps * ev[-1] and abs(o[k, 1] - ev[-1]) <= 100 * eps * ev[-1]
+    # tridiagonal minors skip the reduction (the parameterised families of the experiments use the RandSPD rule)
+    T = sp.diags([-np.ones(199), 1.9999 * np.ones(200), -np.ones(199)], [-1, 0, 1]).toarray()
+    o, lead = ext(T, 150, 0)
+    ev = np.linalg.eigvalsh(lead[:150, :150])
+    assert abs(o[150, 0] - ev[0]) <= 100 * eps * 4.0 and abs(o[150, 1] - ev[-1]) <= 100 * eps * 4.0
+    # a minor with complex eigenvalues: the reference's minimum(eigvals(...)) has no method there -> an error, not a number
+    R = np.array([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+    out = np.zeros(8)
+    assert lib.tk_minor_extremes(capi.dptr(np.asfortranarray(R)), 3, 3, 1, capi.dptr(out)) == -7
+    assert b"complex" in lib.tk_last_error()
