@@ -41,16 +41,29 @@ else:
     b = [one] * d
 flags = {flags}
 out = {{}}
-for label, w, r, u in (("multi", world, rank, uid), ("single", 1, 0, None)):
+for label, w, r, u in (("multi", world, rank, uid), ("multi_nccl", world, rank, uid), ("single", 1, 0, None)):
     if label == "single" and rank != 0:
         continue
+    os.environ["TK_PEER"] = "0" if label == "multi_nccl" else "1"     # read when the exchange buffers are set up
     s = tk.Solver(d, n, nmax, inst, cls, variant, flags=flags, device=rank, rank=r, world=w,
                   unique_id=u)
     s.set_operators([A1] * d); s.set_rhs(b); s.set_schedule(A1, tol)
     res = s.solve(tol)
+    info = s.solve_info()
     lam, fm = s.solution(force=True)
-    out[label] = (res, lam, fm, s.first, s.count)
+    if label == "multi":
+        # the second solve of the handle replays CUDA graphs (with the peer exchange inside): identical histories
+        res2 = s.solve(tol)
+        info2 = s.solve_info()
+        assert info2["graphs_launched"] > 0, info2
+        assert np.array_equal(res2["relres"], res["relres"]) and res2["term_k"] == res["term_k"]
+    out[label] = (res, lam, fm, s.first, s.count, info)
     s.close()
+# the exchange through peer-mapped memory and the NCCL all-gather deliver the same partials: bit-identical solves
+assert out["multi_nccl"][5]["peer_exchange"] is False
+assert np.array_equal(out["multi"][0]["relres"], out["multi_nccl"][0]["relres"])
+assert np.array_equal(out["multi"][0]["projres"], out["multi_nccl"][0]["projres"])
+print("rank", rank, "peer exchange:", out["multi"][5]["peer_exchange"])
 if rank == 0:
     rm, rs = out["multi"][0], out["single"][0]
     assert rm["status"] == rs["status"] and rm["term_k"] == rs["term_k"], (rm["status"], rs["status"])
