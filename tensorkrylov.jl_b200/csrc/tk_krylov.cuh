@@ -219,7 +219,8 @@ __global__ void __launch_bounds__(512) lanczos_ttr_bulk_kernel(KrylovParams p, i
     const bool running = ttr_running(p, k);
     extern __shared__ __align__(16) double smem[];
     __shared__ double scratch[64];
-    __shared__ double slots[2 + 2 * CPM];                     // [0] alpha partial (pulled), [2+2r..] partials pushed by rank r
+    __shared__ double slots[2 + 2 * CPM];                     // [2+2r..] second-round partials pushed by rank r
+    __shared__ double aslots[CPM];                            // first-round partials pushed by rank r
     __shared__ __align__(8) uint64_t bar;
     const int s = blockIdx.x / CPM, part = blockIdx.x % CPM, n = p.n;
     const int chunk = (((n + CPM - 1) / CPM) + 1) & ~1;
@@ -249,6 +250,9 @@ __global__ void __launch_bounds__(512) lanczos_ttr_bulk_kernel(KrylovParams p, i
         if (vkm1) bulk_load(smem + chunk + 2 * TTR_HALO, vkm1 + lo, bytes_s, &bar);
         bulk_load(smem + 2 * chunk + 2 * TTR_HALO, b + lo, bytes_s, &bar);
     }
+    // A CTA may only touch a peer's shared memory once that peer has started: arrive on the cluster barrier now,
+    // wait for it right before the first remote store (by then every peer has long arrived: no time is spent there).
+    if (CPM > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
     int offs[ND];
     double cval[ND];
 #pragma unroll
@@ -256,6 +260,7 @@ __global__ void __launch_bounds__(512) lanczos_ttr_bulk_kernel(KrylovParams p, i
     const double beta_prev = (k >= 2) ? T[2 * p.ncol + (k - 2)] : 0.0;  // H[k-1,k]  (decompositions.jl:78)
     __syncthreads();                                          // the barrier is initialised before anyone polls it
     mbar_wait(&bar, 0);
+    if (CPM > 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
     if (!running) return;
 
     // u = A v_k - beta_{k-1} v_{k-1} for rows lo + threadIdx.x + r * blockDim.x, kept in registers
@@ -277,7 +282,17 @@ __global__ void __launch_bounds__(512) lanczos_ttr_bulk_kernel(KrylovParams p, i
         }
         u[r] = ui;
     }
-    const double alpha = cluster_sum<CPM>(block_sum(acc, scratch), &slots[0]);
+    // first reduction round, pushed like the second one: every CTA stores its partial into all peers, so after the
+    // barrier each CTA reads only its own shared memory (no remote-load latency behind the barrier); summed in rank order
+    double alpha = block_sum(acc, scratch);
+    if (CPM > 1) {
+        cg::cluster_group cl = cg::this_cluster();
+        if (threadIdx.x < CPM) *(cl.map_shared_rank(aslots, threadIdx.x) + part) = alpha;
+        cl.sync();
+        alpha = 0.0;
+#pragma unroll
+        for (int r = 0; r < CPM; ++r) alpha += aslots[r];
+    }
 
     double accb = 0.0;
     acc = 0.0;
@@ -801,10 +816,13 @@ __global__ void __launch_bounds__(THREADS) arnoldi_bgs_kernel(KrylovParams p, in
     for (int pass = 0; pass < 2; ++pass) {
         load_block(ca, 0);
         for (int c0 = 0; c0 < k; c0 += 2 * B) {
-            if (c0 + B < k) load_block(cb, c0 + B);
+            // The next block is requested UNCONDITIONALLY (column indices are clamped to k-1) before the current one is
+            // reduced: behind a branch the compiler sinks the loads below the dot products of the current block, and
+            // every block then pays the full memory latency (measured: 3.5 us per block instead of ~1).
+            load_block(cb, c0 + B);
             process(ca, c0, pass);
             if (c0 + B < k) {
-                if (c0 + 2 * B < k) load_block(ca, c0 + 2 * B);
+                load_block(ca, c0 + 2 * B);
                 process(cb, c0 + B, pass);
             }
         }

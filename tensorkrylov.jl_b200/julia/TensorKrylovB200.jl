@@ -29,6 +29,16 @@ variant_code(::Type{<:TensorLanczos})       = Cint(0)
 variant_code(::Type{<:TensorLanczosReorth}) = Cint(1)
 variant_code(::Type{<:TensorArnoldi})       = Cint(2)
 
+const tables_loaded = Ref(false)
+"The library's own copy of coefficients_data/ (only needed for `spectral = :library`)."
+function load_tables(path::AbstractString = get(ENV, "TENSORKRYLOV_B200_TABLES",
+                                                joinpath(dirname(dirname(pathof(TensorKrylov))), "coefficients_data")))
+    tables_loaded[] && return nothing
+    check(ccall((:tk_tables_load, libtk), Cint, (Cstring,), path))
+    tables_loaded[] = true
+    return nothing
+end
+
 lasterror() = unsafe_string(ccall((:tk_last_error, libtk), Cstring, ()))
 check(rc::Cint) = rc == 0 ? nothing : error("libtensorkrylov_b200: ", lasterror())
 
@@ -56,7 +66,8 @@ Same contract as `tensorkrylov!`: returns the `KruskalTensor` x on convergence, 
 """
 function tensorkrylov_b200!(convergence_data::ConvergenceData{T}, A::KronMat{matT, U}, b::KronProd{T}, tol::T, nmax::Int,
                             orthonormalization_type::Type{<:TensorDecomposition};
-                            device::Int = 0, flags::Cint = TK_FLAG_REFERENCE_H1) where {matT, T<:Float64, U}
+                            device::Int = 0, flags::Cint = TK_FLAG_REFERENCE_H1,
+                            spectral::Symbol = :julia) where {matT, T<:Float64, U}
     d  = length(A)
     ns = Int64.(dimensions(A))
     href = Ref{Ptr{Cvoid}}(C_NULL)
@@ -84,15 +95,23 @@ function tensorkrylov_b200!(convergence_data::ConvergenceData{T}, A::KronMat{mat
             bs = convert(Vector{Float64}, b[s])   # KronProd{T} = Vector{<:AbstractVector{T}}: views are allowed
             check(ccall((:tk_set_rhs, libtk), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Int64), h, s - 1, bs, length(bs)))
         end
-        # exp-sum schedule: exactly the reference's two update_data! calls, hoisted out of the loop
-        # (they depend on A_1, d, tol and k only -- tensor_krylov_method.jl:72-73)
-        spectraldata = SpectralData{matT, T, U}(A, nmax)
-        approxdata   = ApproximationData{T, U}(tol)
-        for k in 2:nmax
-            update_data!(spectraldata, d, A.matrixclass())
-            update_data!(approxdata, spectraldata)
-            check(ccall((:tk_set_schedule, libtk), Cint, (Ptr{Cvoid}, Int32, Float64, Int32, Ptr{Float64}, Ptr{Float64}),
-                        h, k, spectraldata.λ_min[k], length(approxdata.ω), approxdata.α, approxdata.ω))
+        if spectral === :library
+            # the whole schedule inside the library: table lookup and the eigen-extremes of the minors of A_1
+            # (tk_schedule; eigenvalues.jl:335-350 + approximation.jl:160-175), no Julia arithmetic at all
+            load_tables()
+            check(ccall((:tk_schedule, libtk), Cint, (Ptr{Cvoid}, Float64), h, tol))
+        else
+            # exp-sum schedule: exactly the reference's two update_data! calls, hoisted out of the loop
+            # (they depend on A_1, d, tol and k only -- tensor_krylov_method.jl:72-73); lambda_min is then
+            # bit-identical to the reference's
+            spectraldata = SpectralData{matT, T, U}(A, nmax)
+            approxdata   = ApproximationData{T, U}(tol)
+            for k in 2:nmax
+                update_data!(spectraldata, d, A.matrixclass())
+                update_data!(approxdata, spectraldata)
+                check(ccall((:tk_set_schedule, libtk), Cint, (Ptr{Cvoid}, Int32, Float64, Int32, Ptr{Float64}, Ptr{Float64}),
+                            h, k, spectraldata.λ_min[k], length(approxdata.ω), approxdata.α, approxdata.ω))
+            end
         end
         status = Ref{Int32}(0); niter = Ref{Int64}(0); termk = Ref{Int32}(0)
         check(ccall((:tk_solve, libtk), Cint,
