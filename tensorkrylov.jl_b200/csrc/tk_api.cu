@@ -323,7 +323,7 @@ struct tk_handle {
     std::vector<void*> px_opened;
 
     // Krylov state
-    DevBuf<double> V, b, T, Hd, bt, g, S, orthS, bnorm2, vscratch;
+    DevBuf<double> V, b, T, Hd, bt, g, S, orthS, bnorm2, vscratch, gpart;
     DevBuf<int> fallbacks, mode_op_d, status_d, term_k_d, eigfail_d;
     DevBuf<long long> niter_d;
     DevBuf<OpDesc> ops_d;
@@ -717,7 +717,37 @@ static int launch_gram(tk_handle* h, int ncols, int base, int nmodes, int monito
     const double bytes = 8.0 * (double)h->n * (double)ncols * nmodes;
     const int U = env_int("TK_GRAM_U", 4);
     TimedScope ts(h, TM_GRAM, bytes, h->stream);
-    if (w_smem && env_int("TK_GRAM_BALANCED", 1)) {
+    // Three grids.  Column-balanced (one wave, equal column ranges) pays when a CTA's share is long enough to amortise
+    // re-staging the new vector (>= ~32 columns per CTA: 1024 modes per GPU from the 10th column on); below that the
+    // row-sliced form (nothing staged twice, balanced for any mode and column count) takes over.  The (chunks, modes)
+    // grid remains for vectors that do not fit in shared memory.  TK_GRAM_MODE = 0 chunks / 1 balanced / 2 sliced.
+    const int gm = env_int("TK_GRAM_MODE", -1);
+    const bool balanced = gm == 1 || (gm < 0 && (long long)ncols * nmodes >= 32LL * 2 * h->sm_count);
+    const bool sliced = gm == 2 || (gm < 0 && !balanced);
+    if (sliced && h->n >= 64 && (monitor <= 0 || h->vscratch.p)) {
+        SliceMap sm;
+        sm.tiles_per_mode = ((h->n >> 1) + 31) / 32;
+        sm.total = (long long)sm.tiles_per_mode * nmodes;
+        const int grid = (int)std::min<long long>(sm.total, 2LL * h->sm_count);
+        const long long share = std::max<long long>(1, sm.total / grid);
+        sm.smax = (int)(sm.tiles_per_mode / share) + 2;
+        const long long slice_tiles = std::min<long long>(sm.tiles_per_mode, share + 2);
+        const size_t smem_s = ((size_t)((ncols + 1) & ~1) * 8 + ((h->ncol + 1) & ~1) + (size_t)slice_tiles * 64) * 8;
+        if ((size_t)nmodes * sm.smax * h->ncol <= h->gpart.count && smem_s <= smem_limit(h)) {
+#define TK_GRAMS_LAUNCH(UU)                                                                                      \
+            do {                                                                                                 \
+                TK_TRY(allow_smem(gram_row_sliced_kernel<UU, 256>, smem_s));                                     \
+                gram_row_sliced_kernel<UU, 256><<<grid, 256, smem_s, h->stream>>>(h->kp(), ncols, nmodes, base,  \
+                                                          monitor, h->tickets.p, sm, h->gpart.p, h->vscratch.p); \
+            } while (0)
+            if (U == 8) TK_GRAMS_LAUNCH(8); else if (U == 2) TK_GRAMS_LAUNCH(2); else TK_GRAMS_LAUNCH(4);
+#undef TK_GRAMS_LAUNCH
+            h->launches++;
+            TK_CUDA(cudaGetLastError());
+            return 0;
+        }
+    }
+    if (w_smem && balanced) {
         // one wave of resident CTAs, each streaming an equal share of the flat (mode, column) list
         const size_t smem_b = ((size_t)GRAM_BATCH * GRAM_PSTRIDE + ((h->ncol + 1) & ~1) + (size_t)((h->n + 1) & ~1)) * 8;
         int per_sm = (threads == 256 && 2 * (smem_b + 2048) <= 227 * 1024) ? 2 : 1;
@@ -793,6 +823,10 @@ static int launch_arnoldi(tk_handle* h, int k) {
     if (reg_ok && hsm <= 40 * 1024 && env_int("TK_MGS_BLOCK", 1)) {
         if (h->n <= 128 * 4) TK_BGS_LAUNCH(4, 128, 4);
         if (h->n <= 256 * 4) TK_BGS_LAUNCH(4, 256, 4);
+        // one CTA per mode leaves the SM with few warps: more, thinner threads hide the issue latency of the sweep
+        const int bth = env_int("TK_BGS_THREADS", 512);
+        if (h->n <= 1024 * 2 && bth == 1024) TK_BGS_LAUNCH(2, 1024, 4);
+        if (h->n <= 512 * 4 && bth >= 512) TK_BGS_LAUNCH(4, 512, 4);
         if (h->n <= 256 * 8) TK_BGS_LAUNCH(8, 256, 4);
         if (h->n <= 512 * 8) TK_BGS_LAUNCH(8, 512, 2);     // 128 registers per thread at 512 threads: two columns per round
     }
@@ -1028,8 +1062,15 @@ static int enqueue_residual(tk_handle* h, int k) {
     CompressParams c = make_cp(h, k);
     if (h->dl > 0 && h->use_expm) {      // the symmetric path did this inside assemble_cp_kernel
         TimedScope ts(h, TM_ASM, 0.0, h->stream2);
-        gram_blocks_kernel<<<h->dl, 256, 0, h->stream2>>>(c);
-        h->launches++;
+        if ((long long)h->dl * 4 < h->sm_count && (long long)c.t * c.t > 1024 && env_int("TK_GRAM_SPLIT", 1)) {
+            // few modes, many terms: spread Z and the Gram blocks of a mode over many CTAs (two launches)
+            gram_z_kernel<<<dim3(h->dl, (k * c.t + 255) / 256), 256, 0, h->stream2>>>(c);
+            gram_e_kernel<<<dim3(h->dl, (c.t * c.t + 255) / 256), 256, 0, h->stream2>>>(c);
+            h->launches += 2;
+        } else {
+            gram_blocks_kernel<<<h->dl, 256, 0, h->stream2>>>(c);
+            h->launches++;
+        }
         TK_CUDA(cudaGetLastError());
     }
     const long long pst = 5LL * c.t * c.t + 2LL * c.t + 8;
@@ -1139,7 +1180,7 @@ static int prepare(tk_handle* h, bool with_schedule) {
     // working vector of the MGS step when it does not fit in shared memory
     const size_t need_gram = ((size_t)32 * GRAM_PSTRIDE + ((h->ncol + 1) & ~1) + (size_t)h->n) * 8;
     const size_t need_mgs = ((size_t)h->ncol + (size_t)h->n) * 8;
-    if ((need_gram > smem_limit(h) || need_mgs > smem_limit(h)) && !h->vscratch.p) {
+    if ((need_gram > smem_limit(h) || need_mgs > smem_limit(h) || h->variant == TK_LANCZOS_REORTH) && !h->vscratch.p) {
         TK_TRY(h->vscratch.alloc((size_t)h->dk * h->ldv));
         h->cfg_epoch++;
     }
@@ -1411,6 +1452,7 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
     if (variant == TK_ARNOLDI) TK_TRY(h->Hd.alloc(dl * (size_t)h->ncol * h->ncol));
     TK_TRY(h->bt.alloc(dl * (size_t)h->ncol));
     TK_TRY(h->g.alloc(dl * (size_t)h->ncol));
+    TK_TRY(h->gpart.alloc((2 * dl + 2 * (size_t)h->sm_count + 8) * (size_t)h->ncol, false));   // slice partials of the Gram row
     TK_TRY(h->S.alloc(dl));
     TK_TRY(h->orthS.alloc(h->ncol));
     TK_TRY(h->bnorm2.alloc(dl));

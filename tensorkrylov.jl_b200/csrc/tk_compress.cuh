@@ -521,6 +521,61 @@ __global__ void __launch_bounds__(256) gram_blocks_kernel(CompressParams p) {
     gram_blocks_body(p, scratch);
 }
 
+// The same two phases as separate launches with grid = (modes, tiles): one CTA per mode starves the GPU when there
+// are few modes and many exp-sum terms (NonSymInstance at n = 200: d = 5 modes, t = 111 terms, k = 150 -- 12 321
+// Gram entries and 16 650 entries of Z per mode on ONE CTA took 0.9 ms per iteration).
+__global__ void __launch_bounds__(256) gram_z_kernel(CompressParams p) {
+    if (!cta_running(p.status)) return;
+    const int s = blockIdx.x, k = p.k, t = p.t, tld = p.tld;
+    const double* Y = p.Y + (long long)s * p.ystride;
+    double* Z = p.Z + (long long)s * p.ystride;
+    const int idx = blockIdx.y * blockDim.x + threadIdx.x;
+    if (idx >= k * t) return;
+    const int r = idx / t, j = idx % t;
+    double acc = 0.0;
+    if (p.Hd == nullptr) {
+        const double* T = p.T + (long long)s * 3 * p.ncol;
+        if (r > 0) acc = T[p.ncol + (r - 1)] * Y[(long long)(r - 1) * tld + j];
+        acc = fma(T[r], Y[(long long)r * tld + j], acc);
+        if (r < k - 1) acc = fma(T[2 * p.ncol + r], Y[(long long)(r + 1) * tld + j], acc);
+    } else {
+        const double* H = p.Hd + (long long)s * p.ncol * p.ncol;
+        for (int c = max(0, r - 1); c < k; ++c) acc = fma(H[(long long)c * p.ncol + r], Y[(long long)c * tld + j], acc);
+    }
+    Z[(long long)r * tld + j] = acc;
+}
+
+__global__ void __launch_bounds__(256) gram_e_kernel(CompressParams p) {
+    if (!cta_running(p.status)) return;
+    __shared__ double scratch[32];
+    const int s = blockIdx.x, k = p.k, t = p.t, tld = p.tld, tt = t * t;
+    const double* Y = p.Y + (long long)s * p.ystride;
+    const double* Z = p.Z + (long long)s * p.ystride;
+    double* E = p.E + (long long)s * p.estride;
+    const int pidx = blockIdx.y * blockDim.x + threadIdx.x;
+    if (pidx < tt) {
+        const int i = pidx % t, j = pidx / t;
+        double l = 0.0, x = 0.0, lz = 0.0;
+        for (int r = 0; r < k; ++r) {          // same order as gram_blocks_body: bit-identical blocks
+            const double yi = Y[(long long)r * tld + i], yj = Y[(long long)r * tld + j];
+            const double zi = Z[(long long)r * tld + i], zj = Z[(long long)r * tld + j];
+            l = fma(yi, yj, l);
+            x = fma(yi, zj, x);
+            lz = fma(zi, zj, lz);
+        }
+        E[pidx] = l;
+        E[tt + pidx] = x;
+        E[2 * tt + pidx] = lz;
+    }
+    if (blockIdx.y == 0) {
+        const double* bt = p.bt + (long long)s * p.ncol;
+        double acc = 0.0;
+        for (int r = threadIdx.x; r < k; r += blockDim.x) acc = fma(bt[r], bt[r], acc);
+        acc = block_sum(acc, scratch);
+        if (threadIdx.x == 0) p.bb[s] = acc;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Kernel (4b): cross-mode combine.  For each (i,j) the per-mode element
 //     a_q = Ly_q + e X_q[i,j] + h X_q[j,i] + e h Lz_q[i,j]      in R[e,h]/(e^2,h^2)

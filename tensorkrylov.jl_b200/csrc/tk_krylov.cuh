@@ -668,11 +668,7 @@ __global__ void __launch_bounds__(THREADS) arnoldi_mgs_reg_kernel(KrylovParams p
     double* Vs = p.V + (long long)s * p.vstride;
     const double* vk = Vs + (long long)(k - 1) * p.ldv;
     double v[EPT], colr[NB][EPT];
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-        const int i = tid + e * THREADS;
-        v[e] = (i < n) ? apply_row(op, vk, i, n) : 0.0;
-    }
+    apply_rows<EPT, THREADS>(op, vk, n, tid, v);
     int buf = 0;
     auto reduce = [&](double x) -> double {
         x = warp_sum(x);
@@ -745,6 +741,158 @@ __global__ void __launch_bounds__(THREADS) arnoldi_mgs_reg_kernel(KrylovParams p
 }
 
 // ------------------------------------------------------------------------------------------
+// Row-sliced form of the Gram row, for GPUs that hold few modes (128 per GPU at d = 1024 on 8 GPUs, 32 at d = 256,
+// the 50 / 100 modes of configs 2 / 4).  The column-wise grids above give every CTA whole columns, so each CTA must
+// stage the whole new vector (80 KB) however few columns it gets: at 128 modes a CTA streams ~9 columns and re-reads
+// 11-23 % on top, and with few columns whole SMs idle.  Here the rows of all modes form ONE list of 64-row tiles,
+// cut into gridDim.x equal contiguous ranges: a CTA owns a row slice of one mode (two when its range crosses a mode
+// boundary), stages only that slice of the new vector -- no byte is staged twice -- and streams the same slice of
+// EVERY column, one warp per column (two columns in flight per warp; short rows of few columns are cut into
+// sub-slices so all warps work).  Slice partials go to gpart[mode][slice][column]; the CTA that completes a mode
+// (ticket) adds them in slice order -- deterministic -- and runs the monitor.  Balanced to one tile for any mode and
+// column count.
+// ------------------------------------------------------------------------------------------
+struct SliceMap {               // tiles of 32 double2 (64 rows)
+    int tiles_per_mode;         // ceil(nq / 32)
+    long long total;            // nmodes * tiles_per_mode
+    int smax;                   // slices a mode can be cut into: stride of gpart
+};
+
+__device__ __forceinline__ long long slice_begin(const SliceMap& m, int b, int G) { return m.total * b / G; }
+
+// first CTA whose range holds global tile `tile`
+__device__ __forceinline__ int slice_owner(const SliceMap& m, long long tile, int G) {
+    int b = (int)((tile * G) / m.total);
+    while (b + 1 < G && slice_begin(m, b + 1, G) <= tile) ++b;
+    while (b > 0 && slice_begin(m, b, G) > tile) --b;
+    return b;
+}
+
+template <int U, int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 2 : 1)) gram_row_sliced_kernel(KrylovParams p, int ncols, int nmodes, int mode_base,
+                                                              int monitor, unsigned int* tickets, SliceMap sm, double* gpart,
+                                                              double* vscratch) {
+    if (!cta_running(p.status)) return;
+    extern __shared__ double smem[];
+    __shared__ double scratch[32];
+    __shared__ unsigned int my_ticket;
+    const int n = p.n, nq = n >> 1, G = gridDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = THREADS / 32;
+    // sub-slices per column so that every warp has work when there are fewer columns than warps
+    int wpc = 1;
+    while (wpc * 2 * ncols <= NW && wpc < 8) wpc *= 2;
+    const int nitems = ncols * wpc;
+    double* part = smem;                                   // [ncols][8]
+    double* hcol = part + (size_t)((ncols + 1) & ~1) * 8;  // ncol doubles (MGS fallback)
+    double* wsm = hcol + ((p.ncol + 1) & ~1);              // the slice of the new vector
+    long long tile = slice_begin(sm, blockIdx.x, G);
+    const long long tile_end = slice_begin(sm, blockIdx.x + 1, G);
+    while (tile < tile_end) {
+        const int sl_mode = (int)(tile / sm.tiles_per_mode), s = mode_base + sl_mode;
+        const long long mode_t0 = (long long)sl_mode * sm.tiles_per_mode;
+        const int t0 = (int)(tile - mode_t0);
+        const int t1 = (int)min((long long)sm.tiles_per_mode, tile_end - mode_t0);
+        const int q0 = t0 * 32, q1 = min(nq, t1 * 32);          // double2 range of this slice
+        const bool mode_tail = (t1 == sm.tiles_per_mode);       // holds the end of the mode (odd last row)
+        const double* Vs = p.V + (long long)s * p.vstride;
+        const double* wg = Vs + (long long)(ncols - 1) * p.ldv;
+        __syncthreads();                                        // the previous slice's readers of wsm / part are done
+        {
+            const double2* w2g = reinterpret_cast<const double2*>(wg);
+            double2* s2 = reinterpret_cast<double2*>(wsm);
+            for (int q = q0 + threadIdx.x; q < q1; q += THREADS) s2[q - q0] = w2g[q];
+        }
+        __syncthreads();
+        const double2* w2 = reinterpret_cast<const double2*>(wsm);
+        const int len = q1 - q0;
+        const int sublen = (((len + wpc - 1) / wpc) + 31) & ~31;
+        for (int it = warp; it < nitems; it += 2 * NW) {
+            const int itb = it + NW;
+            const bool two = itb < nitems;
+            const int ja = it / wpc, suba = it % wpc, jb = two ? itb / wpc : ja, subb = two ? itb % wpc : suba;
+            const double2* ca = reinterpret_cast<const double2*>(Vs + (long long)ja * p.ldv) + q0;
+            const double2* cb = reinterpret_cast<const double2*>(Vs + (long long)jb * p.ldv) + q0;
+            // both items walk sub-slices of the same length; their offsets differ only when wpc > 1
+            const int oa = suba * sublen, ob = subb * sublen;
+            const int ea = min(len, oa + sublen), eb = min(len, ob + sublen);
+            double a[U], b[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) { a[u] = 0.0; b[u] = 0.0; }
+            int q = lane;
+            const int common = max(0, min(ea - oa, eb - ob));
+            for (; q + 32 * (U - 1) < common; q += 32 * U) {
+                double2 x[U], z[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) x[u] = ld_stream2(ca + oa + q + 32 * u);
+#pragma unroll
+                for (int u = 0; u < U; ++u) z[u] = ld_stream2(cb + ob + q + 32 * u);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const double2 ya = w2[oa + q + 32 * u], yb = w2[ob + q + 32 * u];
+                    a[u] = fma(x[u].x, ya.x, a[u]); a[u] = fma(x[u].y, ya.y, a[u]);
+                    b[u] = fma(z[u].x, yb.x, b[u]); b[u] = fma(z[u].y, yb.y, b[u]);
+                }
+            }
+            for (int qa = q; oa + qa < ea; qa += 32) {
+                const double2 x0 = ld_stream2(ca + oa + qa), y0 = w2[oa + qa];
+                a[0] = fma(x0.x, y0.x, a[0]); a[0] = fma(x0.y, y0.y, a[0]);
+            }
+            if (two)
+                for (int qb = q; ob + qb < eb; qb += 32) {
+                    const double2 z0 = ld_stream2(cb + ob + qb), y0 = w2[ob + qb];
+                    b[0] = fma(z0.x, y0.x, b[0]); b[0] = fma(z0.y, y0.y, b[0]);
+                }
+            if ((n & 1) && mode_tail && lane == 0) {
+                const double wl = wg[n - 1];
+                if (suba == wpc - 1) a[0] = fma(Vs[(long long)ja * p.ldv + n - 1], wl, a[0]);
+                if (two && subb == wpc - 1) b[0] = fma(Vs[(long long)jb * p.ldv + n - 1], wl, b[0]);
+            }
+            double sa = 0.0, sb = 0.0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) { sa += a[u]; sb += b[u]; }
+            sa = warp_sum(sa);
+            sb = warp_sum(sb);
+            if (lane == 0) {
+                part[ja * 8 + suba] = sa;
+                if (two) part[jb * 8 + subb] = sb;
+            }
+        }
+        __syncthreads();
+        // slice index of this CTA inside the mode, number of slices of the mode
+        const int b_first = slice_owner(sm, mode_t0, G);
+        const int b_last = slice_owner(sm, mode_t0 + sm.tiles_per_mode - 1, G);
+        const int slice = blockIdx.x - b_first, nslices = b_last - b_first + 1;
+        double* gp = gpart + ((long long)sl_mode * sm.smax + slice) * p.ncol;
+        for (int j = threadIdx.x; j < ncols; j += THREADS) {
+            double acc = 0.0;
+            for (int sb = 0; sb < wpc; ++sb) acc += part[j * 8 + sb];
+            gp[j] = acc;
+        }
+        tile = mode_t0 + t1;
+        // the CTA that completes the mode adds the slice partials in slice order and runs the monitor
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) my_ticket = atomicAdd(tickets + s, 1u);
+        __syncthreads();
+        if (my_ticket != (unsigned int)(nslices - 1)) continue;
+        __threadfence();
+        double* g = p.g + (long long)s * p.ncol;
+        const double* g0 = gpart + (long long)sl_mode * sm.smax * p.ncol;
+        for (int j = threadIdx.x; j < ncols; j += THREADS) {
+            double acc = 0.0;
+            for (int q = 0; q < nslices; ++q) acc += __ldcg(g0 + (long long)q * p.ncol + j);
+            g[j] = acc;
+        }
+        if (threadIdx.x == 0) tickets[s] = 0u;
+        if (monitor < 0) continue;
+        __threadfence();
+        __syncthreads();
+        monitor_body(p, s, ncols - 1, monitor, hcol, vscratch + (long long)s * p.ldv, scratch);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Blocked form of the Arnoldi step.  Strict MGS is a chain of 2k dependent CTA-wide reductions (~0.35 us each on
 // B200: two shuffle trees, a barrier and the dependent FP64 adds), which bounds arnoldi_mgs_reg_kernel at ~0.3 of
 // the HBM roofline however fast the columns arrive.  Here the basis columns are taken B at a time: the B projections
@@ -769,11 +917,7 @@ __global__ void __launch_bounds__(THREADS) arnoldi_bgs_kernel(KrylovParams p, in
     double* Vs = p.V + (long long)s * p.vstride;
     const double* vk = Vs + (long long)(k - 1) * p.ldv;
     double v[EPT], ca[B][EPT], cb[B][EPT];
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-        const int i = tid + e * THREADS;
-        v[e] = (i < n) ? apply_row(op, vk, i, n) : 0.0;
-    }
+    apply_rows<EPT, THREADS>(op, vk, n, tid, v);
     int buf = 0;
     auto load_block = [&](double (&dst)[B][EPT], int c0) {
 #pragma unroll
