@@ -277,6 +277,7 @@ struct tk_handle {
                          // reference's H_1-for-all-modes rule is on and another rank owns mode 0
     int eig_slot = 0;    // local slot whose T feeds class 0 under TK_FLAG_REFERENCE_H1
     int instance = 0, matrixclass = 0, variant = 0, flags = 0, device = 0, rank = 0, world = 1, sm_count = 148;
+    bool pdl = false;    // programmatic dependent launch between the kernels of the Krylov-step stream
     long long ldv = 0;
     int per_mode = 0, ncls = 1;
     bool use_expm = false;   // compressed solve through the dense exponential (NonSymInstance, and the EigValMat class)
@@ -323,7 +324,7 @@ struct tk_handle {
     std::vector<void*> px_opened;
 
     // Krylov state
-    DevBuf<double> V, b, T, Hd, bt, g, S, orthS, bnorm2, vscratch, gpart;
+    DevBuf<double> V, b, T, Hd, bt, g, S, orthS, bnorm2, vscratch;
     DevBuf<int> fallbacks, mode_op_d, status_d, term_k_d, eigfail_d;
     DevBuf<long long> niter_d;
     DevBuf<OpDesc> ops_d;
@@ -582,11 +583,20 @@ static int launch_ttr_bulk_t(tk_handle* h, int k, int threads, size_t smem) {
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = h->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CPM; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (CPM > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = CPM; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (h->pdl && k >= 2) {       // may start under the tail of the Gram row before it (griddep_wait in the kernel)
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = CPM > 1 ? 1 : 0;
+    cfg.numAttrs = na;
     KrylovParams p = h->kp();
     TK_CUDA(cudaLaunchKernelEx(&cfg, kernel, p, k));
     h->launches++;
@@ -717,36 +727,13 @@ static int launch_gram(tk_handle* h, int ncols, int base, int nmodes, int monito
     const double bytes = 8.0 * (double)h->n * (double)ncols * nmodes;
     const int U = env_int("TK_GRAM_U", 4);
     TimedScope ts(h, TM_GRAM, bytes, h->stream);
-    // Three grids.  Column-balanced (one wave, equal column ranges) pays when a CTA's share is long enough to amortise
-    // re-staging the new vector (>= ~32 columns per CTA: 1024 modes per GPU from the 10th column on); below that the
-    // row-sliced form (nothing staged twice, balanced for any mode and column count) takes over.  The (chunks, modes)
-    // grid remains for vectors that do not fit in shared memory.  TK_GRAM_MODE = 0 chunks / 1 balanced / 2 sliced.
+    // Two grids.  The balanced single-wave form wins when a GPU holds many modes (measured at 1024 modes: 0.95-0.96 of
+    // the HBM peak against 0.93; no tail wave, the new vector re-staged ~4 times per CTA instead of once per 32
+    // columns); with few modes the (chunks, modes) grid is a single wave anyway and its CTAs stage once (256 and 128
+    // modes: 0.82 / 0.75 against 0.75 / 0.63).  A row-sliced grid (nothing staged twice) was measured slower than both
+    // at every size (one warp per column quantises the rounds) and is not kept.  TK_GRAM_MODE = 0 chunks / 1 balanced.
     const int gm = env_int("TK_GRAM_MODE", -1);
-    const bool balanced = gm == 1 || (gm < 0 && (long long)ncols * nmodes >= 32LL * 2 * h->sm_count);
-    const bool sliced = gm == 2 || (gm < 0 && !balanced);
-    if (sliced && h->n >= 64 && (monitor <= 0 || h->vscratch.p)) {
-        SliceMap sm;
-        sm.tiles_per_mode = ((h->n >> 1) + 31) / 32;
-        sm.total = (long long)sm.tiles_per_mode * nmodes;
-        const int grid = (int)std::min<long long>(sm.total, 2LL * h->sm_count);
-        const long long share = std::max<long long>(1, sm.total / grid);
-        sm.smax = (int)(sm.tiles_per_mode / share) + 2;
-        const long long slice_tiles = std::min<long long>(sm.tiles_per_mode, share + 2);
-        const size_t smem_s = ((size_t)((ncols + 1) & ~1) * 8 + ((h->ncol + 1) & ~1) + (size_t)slice_tiles * 64) * 8;
-        if ((size_t)nmodes * sm.smax * h->ncol <= h->gpart.count && smem_s <= smem_limit(h)) {
-#define TK_GRAMS_LAUNCH(UU)                                                                                      \
-            do {                                                                                                 \
-                TK_TRY(allow_smem(gram_row_sliced_kernel<UU, 256>, smem_s));                                     \
-                gram_row_sliced_kernel<UU, 256><<<grid, 256, smem_s, h->stream>>>(h->kp(), ncols, nmodes, base,  \
-                                                          monitor, h->tickets.p, sm, h->gpart.p, h->vscratch.p); \
-            } while (0)
-            if (U == 8) TK_GRAMS_LAUNCH(8); else if (U == 2) TK_GRAMS_LAUNCH(2); else TK_GRAMS_LAUNCH(4);
-#undef TK_GRAMS_LAUNCH
-            h->launches++;
-            TK_CUDA(cudaGetLastError());
-            return 0;
-        }
-    }
+    const bool balanced = gm == 1 || (gm < 0 && nmodes >= 512);
     if (w_smem && balanced) {
         // one wave of resident CTAs, each streaming an equal share of the flat (mode, column) list
         const size_t smem_b = ((size_t)GRAM_BATCH * GRAM_PSTRIDE + ((h->ncol + 1) & ~1) + (size_t)((h->n + 1) & ~1)) * 8;
@@ -757,8 +744,14 @@ static int launch_gram(tk_handle* h, int ncols, int base, int nmodes, int monito
 #define TK_GRAMB_LAUNCH(UU, TT)                                                                                  \
         do {                                                                                                     \
             TK_TRY(allow_smem(gram_row_balanced_kernel<UU, TT>, smem_b));                                        \
-            gram_row_balanced_kernel<UU, TT><<<grid, TT, smem_b, h->stream>>>(h->kp(), ncols, nmodes, base, wpc, \
-                                                                              monitor, h->tickets.p);            \
+            cudaLaunchConfig_t cfg = {};                                                                         \
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TT); cfg.dynamicSmemBytes = smem_b; cfg.stream = h->stream; \
+            cudaLaunchAttribute at[1];                                                                           \
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                       \
+            at[0].val.programmaticStreamSerializationAllowed = 1;                                                \
+            cfg.attrs = at; cfg.numAttrs = (h->pdl && ncols > 1) ? 1 : 0;                                        \
+            TK_CUDA(cudaLaunchKernelEx(&cfg, gram_row_balanced_kernel<UU, TT>, h->kp(), ncols, nmodes, base, wpc, \
+                                       monitor, h->tickets.p));                                                  \
         } while (0)
         if (threads == 512) {
             if (U == 8) TK_GRAMB_LAUNCH(8, 512); else if (U == 2) TK_GRAMB_LAUNCH(2, 512); else TK_GRAMB_LAUNCH(4, 512);
@@ -773,9 +766,14 @@ static int launch_gram(tk_handle* h, int ncols, int base, int nmodes, int monito
 #define TK_GRAM_LAUNCH(UU, TT)                                                                                   \
     do {                                                                                                         \
         TK_TRY(allow_smem(gram_row_kernel<UU, TT>, smem));                                                       \
-        gram_row_kernel<UU, TT><<<dim3(nchunks, nmodes), TT, smem, h->stream>>>(h->kp(), ncols, cpc, base,       \
-                                                                                w_smem ? 1 : 0, wpc, monitor,    \
-                                                                                h->tickets.p, h->vscratch.p);    \
+        cudaLaunchConfig_t cfg = {};                                                                             \
+        cfg.gridDim = dim3(nchunks, nmodes); cfg.blockDim = dim3(TT); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream; \
+        cudaLaunchAttribute at[1];                                                                               \
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                           \
+        at[0].val.programmaticStreamSerializationAllowed = 1;                                                    \
+        cfg.attrs = at; cfg.numAttrs = (h->pdl && ncols > 1) ? 1 : 0;                                            \
+        TK_CUDA(cudaLaunchKernelEx(&cfg, gram_row_kernel<UU, TT>, h->kp(), ncols, cpc, base, w_smem ? 1 : 0, wpc, \
+                                   monitor, h->tickets.p, h->vscratch.p));                                       \
     } while (0)
     if (threads == 512) {
         if (U == 8) TK_GRAM_LAUNCH(8, 512); else if (U == 2) TK_GRAM_LAUNCH(2, 512); else TK_GRAM_LAUNCH(4, 512);
@@ -1180,7 +1178,7 @@ static int prepare(tk_handle* h, bool with_schedule) {
     // working vector of the MGS step when it does not fit in shared memory
     const size_t need_gram = ((size_t)32 * GRAM_PSTRIDE + ((h->ncol + 1) & ~1) + (size_t)h->n) * 8;
     const size_t need_mgs = ((size_t)h->ncol + (size_t)h->n) * 8;
-    if ((need_gram > smem_limit(h) || need_mgs > smem_limit(h) || h->variant == TK_LANCZOS_REORTH) && !h->vscratch.p) {
+    if ((need_gram > smem_limit(h) || need_mgs > smem_limit(h)) && !h->vscratch.p) {
         TK_TRY(h->vscratch.alloc((size_t)h->dk * h->ldv));
         h->cfg_epoch++;
     }
@@ -1429,6 +1427,7 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
     h->eig_slot = shadow ? h->dl : 0;
 
     TK_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
+    h->pdl = env_int("TK_PDL", 0) != 0 && !(flags & (TK_FLAG_TIME_KERNELS | TK_FLAG_TIME_ALL));
     TK_TRY(acquire_resources(device, &h->res));
     tk_resources* r = h->res;
     h->stream = r->s_main;
@@ -1452,7 +1451,6 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
     if (variant == TK_ARNOLDI) TK_TRY(h->Hd.alloc(dl * (size_t)h->ncol * h->ncol));
     TK_TRY(h->bt.alloc(dl * (size_t)h->ncol));
     TK_TRY(h->g.alloc(dl * (size_t)h->ncol));
-    TK_TRY(h->gpart.alloc((2 * dl + 2 * (size_t)h->sm_count + 8) * (size_t)h->ncol, false));   // slice partials of the Gram row
     TK_TRY(h->S.alloc(dl));
     TK_TRY(h->orthS.alloc(h->ncol));
     TK_TRY(h->bnorm2.alloc(dl));

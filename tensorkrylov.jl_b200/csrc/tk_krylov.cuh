@@ -216,6 +216,7 @@ template <int CPM, int ND, bool CONSTD, int RPT>
 __global__ void __launch_bounds__(512) lanczos_ttr_bulk_kernel(KrylovParams p, int k) {
     // the snapshot is only consumed after the bulk loads have been issued (and have landed): its latency is off the
     // critical path, and a skipped launch merely fetches three slices it does not use
+    griddep_launch();          // the Gram row behind this step may be placed while this grid drains
     const bool running = ttr_running(p, k);
     extern __shared__ __align__(16) double smem[];
     __shared__ double scratch[64];
@@ -246,10 +247,14 @@ __global__ void __launch_bounds__(512) lanczos_ttr_bulk_kernel(KrylovParams p, i
         const uint32_t bytes_v = (uint32_t)(g1 - g0) * 8u, bytes_s = (uint32_t)(he - lo) * 8u;
         const uint32_t total = bytes_v + bytes_s * (vkm1 ? 2u : 1u);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(&bar)), "r"(total) : "memory");
-        bulk_load(smem + (g0 - lo + TTR_HALO), vk + g0, bytes_v, &bar);
+        // v_{k-1} and b are final: fetch them before waiting for the preceding grid (the Gram row of iteration k-1,
+        // whose monitor may still replace v_k and H[k-1,k] by the MGS fallback); v_k only after it
         if (vkm1) bulk_load(smem + chunk + 2 * TTR_HALO, vkm1 + lo, bytes_s, &bar);
         bulk_load(smem + 2 * chunk + 2 * TTR_HALO, b + lo, bytes_s, &bar);
+        griddep_wait();
+        bulk_load(smem + (g0 - lo + TTR_HALO), vk + g0, bytes_v, &bar);
     }
+    griddep_wait();
     // A CTA may only touch a peer's shared memory once that peer has started: arrive on the cluster barrier now,
     // wait for it right before the first remote store (by then every peer has long arrived: no time is spent there).
     if (CPM > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
@@ -440,6 +445,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 2 : 1)) gram_row_ke
                                                        unsigned int* tickets, double* vscratch) {
     // wpc = warps that share one column: every column is cut into wpc contiguous segments so all warps of the
     // CTA stream equal amounts, whatever the number of columns.
+    griddep_wait();            // reads the column the preceding 3-term step wrote; see gram_row_balanced_kernel
+    griddep_launch();
     if (!cta_running(p.status)) return;
     extern __shared__ double smem[];
     const int s = mode_base + blockIdx.y, n = p.n;
@@ -546,6 +553,11 @@ constexpr int GRAM_BATCH = 32;     // columns per pass of a CTA (size of its par
 template <int U, int THREADS>
 __global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 2 : 1)) gram_row_balanced_kernel(KrylovParams p, int ncols, int nmodes,
                                                                 int mode_base, int wpc, int monitor, unsigned int* tickets) {
+    // This grid reads the column the preceding 3-term step wrote.  Only then may the 3-term step of the NEXT iteration
+    // be placed (it prefetches v_k and b while this grid drains): releasing it earlier would let it run ahead of a
+    // Gram row two launches back whose MGS fallback may still be replacing v_k.
+    griddep_wait();
+    griddep_launch();
     if (!cta_running(p.status)) return;
     extern __shared__ double smem[];
     __shared__ double scratch[32];
@@ -737,158 +749,6 @@ __global__ void __launch_bounds__(THREADS) arnoldi_mgs_reg_kernel(KrylovParams p
         double* T = p.T + (long long)s * 3 * p.ncol;
         T[k - 1] = hcol[k - 1];
         T[p.ncol + (k - 1)] = beta;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// Row-sliced form of the Gram row, for GPUs that hold few modes (128 per GPU at d = 1024 on 8 GPUs, 32 at d = 256,
-// the 50 / 100 modes of configs 2 / 4).  The column-wise grids above give every CTA whole columns, so each CTA must
-// stage the whole new vector (80 KB) however few columns it gets: at 128 modes a CTA streams ~9 columns and re-reads
-// 11-23 % on top, and with few columns whole SMs idle.  Here the rows of all modes form ONE list of 64-row tiles,
-// cut into gridDim.x equal contiguous ranges: a CTA owns a row slice of one mode (two when its range crosses a mode
-// boundary), stages only that slice of the new vector -- no byte is staged twice -- and streams the same slice of
-// EVERY column, one warp per column (two columns in flight per warp; short rows of few columns are cut into
-// sub-slices so all warps work).  Slice partials go to gpart[mode][slice][column]; the CTA that completes a mode
-// (ticket) adds them in slice order -- deterministic -- and runs the monitor.  Balanced to one tile for any mode and
-// column count.
-// ------------------------------------------------------------------------------------------
-struct SliceMap {               // tiles of 32 double2 (64 rows)
-    int tiles_per_mode;         // ceil(nq / 32)
-    long long total;            // nmodes * tiles_per_mode
-    int smax;                   // slices a mode can be cut into: stride of gpart
-};
-
-__device__ __forceinline__ long long slice_begin(const SliceMap& m, int b, int G) { return m.total * b / G; }
-
-// first CTA whose range holds global tile `tile`
-__device__ __forceinline__ int slice_owner(const SliceMap& m, long long tile, int G) {
-    int b = (int)((tile * G) / m.total);
-    while (b + 1 < G && slice_begin(m, b + 1, G) <= tile) ++b;
-    while (b > 0 && slice_begin(m, b, G) > tile) --b;
-    return b;
-}
-
-template <int U, int THREADS>
-__global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 2 : 1)) gram_row_sliced_kernel(KrylovParams p, int ncols, int nmodes, int mode_base,
-                                                              int monitor, unsigned int* tickets, SliceMap sm, double* gpart,
-                                                              double* vscratch) {
-    if (!cta_running(p.status)) return;
-    extern __shared__ double smem[];
-    __shared__ double scratch[32];
-    __shared__ unsigned int my_ticket;
-    const int n = p.n, nq = n >> 1, G = gridDim.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int NW = THREADS / 32;
-    // sub-slices per column so that every warp has work when there are fewer columns than warps
-    int wpc = 1;
-    while (wpc * 2 * ncols <= NW && wpc < 8) wpc *= 2;
-    const int nitems = ncols * wpc;
-    double* part = smem;                                   // [ncols][8]
-    double* hcol = part + (size_t)((ncols + 1) & ~1) * 8;  // ncol doubles (MGS fallback)
-    double* wsm = hcol + ((p.ncol + 1) & ~1);              // the slice of the new vector
-    long long tile = slice_begin(sm, blockIdx.x, G);
-    const long long tile_end = slice_begin(sm, blockIdx.x + 1, G);
-    while (tile < tile_end) {
-        const int sl_mode = (int)(tile / sm.tiles_per_mode), s = mode_base + sl_mode;
-        const long long mode_t0 = (long long)sl_mode * sm.tiles_per_mode;
-        const int t0 = (int)(tile - mode_t0);
-        const int t1 = (int)min((long long)sm.tiles_per_mode, tile_end - mode_t0);
-        const int q0 = t0 * 32, q1 = min(nq, t1 * 32);          // double2 range of this slice
-        const bool mode_tail = (t1 == sm.tiles_per_mode);       // holds the end of the mode (odd last row)
-        const double* Vs = p.V + (long long)s * p.vstride;
-        const double* wg = Vs + (long long)(ncols - 1) * p.ldv;
-        __syncthreads();                                        // the previous slice's readers of wsm / part are done
-        {
-            const double2* w2g = reinterpret_cast<const double2*>(wg);
-            double2* s2 = reinterpret_cast<double2*>(wsm);
-            for (int q = q0 + threadIdx.x; q < q1; q += THREADS) s2[q - q0] = w2g[q];
-        }
-        __syncthreads();
-        const double2* w2 = reinterpret_cast<const double2*>(wsm);
-        const int len = q1 - q0;
-        const int sublen = (((len + wpc - 1) / wpc) + 31) & ~31;
-        for (int it = warp; it < nitems; it += 2 * NW) {
-            const int itb = it + NW;
-            const bool two = itb < nitems;
-            const int ja = it / wpc, suba = it % wpc, jb = two ? itb / wpc : ja, subb = two ? itb % wpc : suba;
-            const double2* ca = reinterpret_cast<const double2*>(Vs + (long long)ja * p.ldv) + q0;
-            const double2* cb = reinterpret_cast<const double2*>(Vs + (long long)jb * p.ldv) + q0;
-            // both items walk sub-slices of the same length; their offsets differ only when wpc > 1
-            const int oa = suba * sublen, ob = subb * sublen;
-            const int ea = min(len, oa + sublen), eb = min(len, ob + sublen);
-            double a[U], b[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) { a[u] = 0.0; b[u] = 0.0; }
-            int q = lane;
-            const int common = max(0, min(ea - oa, eb - ob));
-            for (; q + 32 * (U - 1) < common; q += 32 * U) {
-                double2 x[U], z[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) x[u] = ld_stream2(ca + oa + q + 32 * u);
-#pragma unroll
-                for (int u = 0; u < U; ++u) z[u] = ld_stream2(cb + ob + q + 32 * u);
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const double2 ya = w2[oa + q + 32 * u], yb = w2[ob + q + 32 * u];
-                    a[u] = fma(x[u].x, ya.x, a[u]); a[u] = fma(x[u].y, ya.y, a[u]);
-                    b[u] = fma(z[u].x, yb.x, b[u]); b[u] = fma(z[u].y, yb.y, b[u]);
-                }
-            }
-            for (int qa = q; oa + qa < ea; qa += 32) {
-                const double2 x0 = ld_stream2(ca + oa + qa), y0 = w2[oa + qa];
-                a[0] = fma(x0.x, y0.x, a[0]); a[0] = fma(x0.y, y0.y, a[0]);
-            }
-            if (two)
-                for (int qb = q; ob + qb < eb; qb += 32) {
-                    const double2 z0 = ld_stream2(cb + ob + qb), y0 = w2[ob + qb];
-                    b[0] = fma(z0.x, y0.x, b[0]); b[0] = fma(z0.y, y0.y, b[0]);
-                }
-            if ((n & 1) && mode_tail && lane == 0) {
-                const double wl = wg[n - 1];
-                if (suba == wpc - 1) a[0] = fma(Vs[(long long)ja * p.ldv + n - 1], wl, a[0]);
-                if (two && subb == wpc - 1) b[0] = fma(Vs[(long long)jb * p.ldv + n - 1], wl, b[0]);
-            }
-            double sa = 0.0, sb = 0.0;
-#pragma unroll
-            for (int u = 0; u < U; ++u) { sa += a[u]; sb += b[u]; }
-            sa = warp_sum(sa);
-            sb = warp_sum(sb);
-            if (lane == 0) {
-                part[ja * 8 + suba] = sa;
-                if (two) part[jb * 8 + subb] = sb;
-            }
-        }
-        __syncthreads();
-        // slice index of this CTA inside the mode, number of slices of the mode
-        const int b_first = slice_owner(sm, mode_t0, G);
-        const int b_last = slice_owner(sm, mode_t0 + sm.tiles_per_mode - 1, G);
-        const int slice = blockIdx.x - b_first, nslices = b_last - b_first + 1;
-        double* gp = gpart + ((long long)sl_mode * sm.smax + slice) * p.ncol;
-        for (int j = threadIdx.x; j < ncols; j += THREADS) {
-            double acc = 0.0;
-            for (int sb = 0; sb < wpc; ++sb) acc += part[j * 8 + sb];
-            gp[j] = acc;
-        }
-        tile = mode_t0 + t1;
-        // the CTA that completes the mode adds the slice partials in slice order and runs the monitor
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) my_ticket = atomicAdd(tickets + s, 1u);
-        __syncthreads();
-        if (my_ticket != (unsigned int)(nslices - 1)) continue;
-        __threadfence();
-        double* g = p.g + (long long)s * p.ncol;
-        const double* g0 = gpart + (long long)sl_mode * sm.smax * p.ncol;
-        for (int j = threadIdx.x; j < ncols; j += THREADS) {
-            double acc = 0.0;
-            for (int q = 0; q < nslices; ++q) acc += __ldcg(g0 + (long long)q * p.ncol + j);
-            g[j] = acc;
-        }
-        if (threadIdx.x == 0) tickets[s] = 0u;
-        if (monitor < 0) continue;
-        __threadfence();
-        __syncthreads();
-        monitor_body(p, s, ncols - 1, monitor, hcol, vscratch + (long long)s * p.ldv, scratch);
     }
 }
 
