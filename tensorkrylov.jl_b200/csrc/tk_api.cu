@@ -277,7 +277,6 @@ struct tk_handle {
                          // reference's H_1-for-all-modes rule is on and another rank owns mode 0
     int eig_slot = 0;    // local slot whose T feeds class 0 under TK_FLAG_REFERENCE_H1
     int instance = 0, matrixclass = 0, variant = 0, flags = 0, device = 0, rank = 0, world = 1, sm_count = 148;
-    bool pdl = false;    // programmatic dependent launch between the kernels of the Krylov-step stream
     long long ldv = 0;
     int per_mode = 0, ncls = 1;
     bool use_expm = false;   // compressed solve through the dense exponential (NonSymInstance, and the EigValMat class)
@@ -583,16 +582,11 @@ static int launch_ttr_bulk_t(tk_handle* h, int k, int threads, size_t smem) {
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = h->stream;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[1];
     int na = 0;
     if (CPM > 1) {
         attr[na].id = cudaLaunchAttributeClusterDimension;
         attr[na].val.clusterDim.x = CPM; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
-        ++na;
-    }
-    if (h->pdl && k >= 2) {       // may start under the tail of the Gram row before it (griddep_wait in the kernel)
-        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[na].val.programmaticStreamSerializationAllowed = 1;
         ++na;
     }
     cfg.attrs = attr;
@@ -744,14 +738,8 @@ static int launch_gram(tk_handle* h, int ncols, int base, int nmodes, int monito
 #define TK_GRAMB_LAUNCH(UU, TT)                                                                                  \
         do {                                                                                                     \
             TK_TRY(allow_smem(gram_row_balanced_kernel<UU, TT>, smem_b));                                        \
-            cudaLaunchConfig_t cfg = {};                                                                         \
-            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TT); cfg.dynamicSmemBytes = smem_b; cfg.stream = h->stream; \
-            cudaLaunchAttribute at[1];                                                                           \
-            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                       \
-            at[0].val.programmaticStreamSerializationAllowed = 1;                                                \
-            cfg.attrs = at; cfg.numAttrs = (h->pdl && ncols > 1) ? 1 : 0;                                        \
-            TK_CUDA(cudaLaunchKernelEx(&cfg, gram_row_balanced_kernel<UU, TT>, h->kp(), ncols, nmodes, base, wpc, \
-                                       monitor, h->tickets.p));                                                  \
+            gram_row_balanced_kernel<UU, TT><<<grid, TT, smem_b, h->stream>>>(h->kp(), ncols, nmodes, base, wpc, \
+                                                                              monitor, h->tickets.p);            \
         } while (0)
         if (threads == 512) {
             if (U == 8) TK_GRAMB_LAUNCH(8, 512); else if (U == 2) TK_GRAMB_LAUNCH(2, 512); else TK_GRAMB_LAUNCH(4, 512);
@@ -766,14 +754,9 @@ static int launch_gram(tk_handle* h, int ncols, int base, int nmodes, int monito
 #define TK_GRAM_LAUNCH(UU, TT)                                                                                   \
     do {                                                                                                         \
         TK_TRY(allow_smem(gram_row_kernel<UU, TT>, smem));                                                       \
-        cudaLaunchConfig_t cfg = {};                                                                             \
-        cfg.gridDim = dim3(nchunks, nmodes); cfg.blockDim = dim3(TT); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream; \
-        cudaLaunchAttribute at[1];                                                                               \
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                           \
-        at[0].val.programmaticStreamSerializationAllowed = 1;                                                    \
-        cfg.attrs = at; cfg.numAttrs = (h->pdl && ncols > 1) ? 1 : 0;                                            \
-        TK_CUDA(cudaLaunchKernelEx(&cfg, gram_row_kernel<UU, TT>, h->kp(), ncols, cpc, base, w_smem ? 1 : 0, wpc, \
-                                   monitor, h->tickets.p, h->vscratch.p));                                       \
+        gram_row_kernel<UU, TT><<<dim3(nchunks, nmodes), TT, smem, h->stream>>>(h->kp(), ncols, cpc, base,       \
+                                                                                w_smem ? 1 : 0, wpc, monitor,    \
+                                                                                h->tickets.p, h->vscratch.p);    \
     } while (0)
     if (threads == 512) {
         if (U == 8) TK_GRAM_LAUNCH(8, 512); else if (U == 2) TK_GRAM_LAUNCH(2, 512); else TK_GRAM_LAUNCH(4, 512);
@@ -1427,7 +1410,6 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
     h->eig_slot = shadow ? h->dl : 0;
 
     TK_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
-    h->pdl = env_int("TK_PDL", 0) != 0 && !(flags & (TK_FLAG_TIME_KERNELS | TK_FLAG_TIME_ALL));
     TK_TRY(acquire_resources(device, &h->res));
     tk_resources* r = h->res;
     h->stream = r->s_main;

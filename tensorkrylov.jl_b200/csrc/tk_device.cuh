@@ -105,13 +105,6 @@ __device__ __forceinline__ double apply_row(const OpDesc& op, const double* __re
     return acc;
 }
 
-// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute may start
-// while its predecessor on the stream is still draining; it must not touch the predecessor's results before
-// griddep_wait() (which returns at once when the launch carries no such dependency).  griddep_launch() in the
-// predecessor lets the successor's CTAs be placed as soon as every CTA of the predecessor has called it.
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
 // Run/skip decision of a whole CTA.  finalize flips the status word from another stream while kernels of later
 // iterations are in flight, so threads that each read the live word could disagree and part of a CTA would miss the
 // barriers below; thread 0 reads it once and every thread takes that reading.

@@ -216,7 +216,6 @@ template <int CPM, int ND, bool CONSTD, int RPT>
 __global__ void __launch_bounds__(512) lanczos_ttr_bulk_kernel(KrylovParams p, int k) {
     // the snapshot is only consumed after the bulk loads have been issued (and have landed): its latency is off the
     // critical path, and a skipped launch merely fetches three slices it does not use
-    griddep_launch();          // the Gram row behind this step may be placed while this grid drains
     const bool running = ttr_running(p, k);
     extern __shared__ __align__(16) double smem[];
     __shared__ double scratch[64];
@@ -247,14 +246,10 @@ __global__ void __launch_bounds__(512) lanczos_ttr_bulk_kernel(KrylovParams p, i
         const uint32_t bytes_v = (uint32_t)(g1 - g0) * 8u, bytes_s = (uint32_t)(he - lo) * 8u;
         const uint32_t total = bytes_v + bytes_s * (vkm1 ? 2u : 1u);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(&bar)), "r"(total) : "memory");
-        // v_{k-1} and b are final: fetch them before waiting for the preceding grid (the Gram row of iteration k-1,
-        // whose monitor may still replace v_k and H[k-1,k] by the MGS fallback); v_k only after it
+        bulk_load(smem + (g0 - lo + TTR_HALO), vk + g0, bytes_v, &bar);
         if (vkm1) bulk_load(smem + chunk + 2 * TTR_HALO, vkm1 + lo, bytes_s, &bar);
         bulk_load(smem + 2 * chunk + 2 * TTR_HALO, b + lo, bytes_s, &bar);
-        griddep_wait();
-        bulk_load(smem + (g0 - lo + TTR_HALO), vk + g0, bytes_v, &bar);
     }
-    griddep_wait();
     // A CTA may only touch a peer's shared memory once that peer has started: arrive on the cluster barrier now,
     // wait for it right before the first remote store (by then every peer has long arrived: no time is spent there).
     if (CPM > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
@@ -445,8 +440,6 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 2 : 1)) gram_row_ke
                                                        unsigned int* tickets, double* vscratch) {
     // wpc = warps that share one column: every column is cut into wpc contiguous segments so all warps of the
     // CTA stream equal amounts, whatever the number of columns.
-    griddep_wait();            // reads the column the preceding 3-term step wrote; see gram_row_balanced_kernel
-    griddep_launch();
     if (!cta_running(p.status)) return;
     extern __shared__ double smem[];
     const int s = mode_base + blockIdx.y, n = p.n;
@@ -553,11 +546,6 @@ constexpr int GRAM_BATCH = 32;     // columns per pass of a CTA (size of its par
 template <int U, int THREADS>
 __global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 2 : 1)) gram_row_balanced_kernel(KrylovParams p, int ncols, int nmodes,
                                                                 int mode_base, int wpc, int monitor, unsigned int* tickets) {
-    // This grid reads the column the preceding 3-term step wrote.  Only then may the 3-term step of the NEXT iteration
-    // be placed (it prefetches v_k and b while this grid drains): releasing it earlier would let it run ahead of a
-    // Gram row two launches back whose MGS fallback may still be replacing v_k.
-    griddep_wait();
-    griddep_launch();
     if (!cta_running(p.status)) return;
     extern __shared__ double smem[];
     __shared__ double scratch[32];
