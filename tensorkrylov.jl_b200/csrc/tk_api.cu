@@ -224,6 +224,7 @@ struct tk_resources {
 static std::vector<tk_resources*> g_res_free;
 static std::map<size_t, std::vector<void*>> g_host_pool;   // parked page-locked blocks of tk_alloc_host, by size
 static std::map<void*, size_t> g_host_live;
+static std::map<std::string, void*> g_ipc_open;            // peer buffers mapped through CUDA IPC, by exported handle
 
 static int acquire_resources(int device, tk_resources** out) {
     {
@@ -265,7 +266,6 @@ struct tk_handle {
     tk_resources* res = nullptr;
     ~tk_handle() {
         for (auto& sg : segs) if (sg.exec) cudaGraphExecDestroy(sg.exec);
-        for (void* q : px_opened) cudaIpcCloseMemHandle(q);
         if (res) {                      // also on a failed tk_create
             res->ev_pool.swap(ev_pool);
             std::lock_guard<std::mutex> lock(g_mutex);
@@ -320,7 +320,6 @@ struct tk_handle {
     bool px_ready = false;
     DevBuf<double> px_recv;
     DevBuf<unsigned long long> px_flags;
-    std::vector<void*> px_opened;
 
     // Krylov state
     DevBuf<double> V, b, T, Hd, bt, g, S, orthS, bnorm2, vscratch;
@@ -713,7 +712,7 @@ static int launch_gram(tk_handle* h, int ncols, int base, int nmodes, int monito
     nchunks = (ncols + cpc - 1) / cpc;
     const size_t fixed = ((size_t)cpc * GRAM_PSTRIDE + ((h->ncol + 1) & ~1)) * 8;
     size_t smem = fixed + (size_t)h->n * 8;
-    const bool w_smem = smem <= smem_limit(h);
+    const bool w_smem = smem <= smem_limit(h) && env_int("TK_GRAM_WSMEM", 1) != 0;
     if (!w_smem) {
         smem = fixed;
         if (monitor > 0 && !h->vscratch.p) TK_TRY(h->vscratch.alloc((size_t)h->dk * h->ldv));
@@ -1091,8 +1090,6 @@ static int enqueue_residual(tk_handle* h, int k) {
 // ranks must agree on the path, so the outcome is voted on (a second all-gather); if any rank could not map a
 // peer the solve keeps NCCL's all-gather.  Collective: called by all ranks from the first tk_solve / tk_compress.
 static int setup_peer_exchange(tk_handle* h) {
-    for (void* q : h->px_opened) cudaIpcCloseMemHandle(q);
-    h->px_opened.clear();
     h->px_ready = false;
     if (h->world > PX_MAX || !env_int("TK_PEER", 1)) return 0;
     const long long slot = (h->pstride_max + 1) & ~1LL;
@@ -1122,13 +1119,21 @@ static int setup_peer_exchange(tk_handle* h) {
     px.world = h->world; px.rank = h->rank; px.slot_stride = slot;
     bool ok = true;
     for (int r = 0; r < h->world; ++r) ok = ok && all[r].ok;
+    // Mappings are kept for the life of the process, keyed by the exported handle: a peer whose next solver gets
+    // the same cached device blocks exports the same handles, and opening one costs ~0.1 ms (14 per rank at N = 8).
+    auto open_cached = [&](const cudaIpcMemHandle_t& mh, void** out) -> bool {
+        const std::string key(reinterpret_cast<const char*>(&mh), sizeof(mh));
+        std::lock_guard<std::mutex> lock(g_mutex);
+        auto it = g_ipc_open.find(key);
+        if (it != g_ipc_open.end()) { *out = it->second; return true; }
+        if (cudaIpcOpenMemHandle(out, mh, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) return false;
+        g_ipc_open[key] = *out;
+        return true;
+    };
     for (int r = 0; r < h->world && ok; ++r) {
         if (r == h->rank) { px.recv[r] = h->px_recv.p; px.flag[r] = h->px_flags.p; continue; }
         void *pr = nullptr, *pf = nullptr;
-        if (cudaIpcOpenMemHandle(&pr, all[r].recv, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
-        h->px_opened.push_back(pr);
-        if (cudaIpcOpenMemHandle(&pf, all[r].flag, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
-        h->px_opened.push_back(pf);
+        if (!open_cached(all[r].recv, &pr) || !open_cached(all[r].flag, &pf)) { ok = false; break; }
         px.recv[r] = static_cast<double*>(pr);
         px.flag[r] = static_cast<unsigned long long*>(pf);
     }
@@ -1137,8 +1142,6 @@ static int setup_peer_exchange(tk_handle* h) {
     TK_TRY(gather());                       // vote: also orders every rank's mapping before anybody's first store
     for (int r = 0; r < h->world; ++r) ok = ok && all[r].ok;
     if (!ok) {
-        for (void* q : h->px_opened) cudaIpcCloseMemHandle(q);
-        h->px_opened.clear();
         cudaGetLastError();
         if (env_int("TK_PEER", 1) == 2) return set_error(TK_ECUDA, "peer mapping of the exchange buffers failed (TK_PEER=2 forbids the NCCL fallback)");
         return 0;
@@ -1161,7 +1164,7 @@ static int prepare(tk_handle* h, bool with_schedule) {
     // working vector of the MGS step when it does not fit in shared memory
     const size_t need_gram = ((size_t)32 * GRAM_PSTRIDE + ((h->ncol + 1) & ~1) + (size_t)h->n) * 8;
     const size_t need_mgs = ((size_t)h->ncol + (size_t)h->n) * 8;
-    if ((need_gram > smem_limit(h) || need_mgs > smem_limit(h)) && !h->vscratch.p) {
+    if ((need_gram > smem_limit(h) || need_mgs > smem_limit(h) || !env_int("TK_GRAM_WSMEM", 1)) && !h->vscratch.p) {
         TK_TRY(h->vscratch.alloc((size_t)h->dk * h->ldv));
         h->cfg_epoch++;
     }
@@ -1503,6 +1506,8 @@ int tk_release_cache(void) {
         delete r;
     }
     g_res_free.clear();
+    for (auto& kv : g_ipc_open) cudaIpcCloseMemHandle(kv.second);
+    g_ipc_open.clear();
     for (auto& kv : g_host_pool)
         for (void* q : kv.second) cudaFreeHost(q);
     g_host_pool.clear();
