@@ -712,7 +712,9 @@ static int launch_gram(tk_handle* h, int ncols, int base, int nmodes, int monito
     nchunks = (ncols + cpc - 1) / cpc;
     const size_t fixed = ((size_t)cpc * GRAM_PSTRIDE + ((h->ncol + 1) & ~1)) * 8;
     size_t smem = fixed + (size_t)h->n * 8;
-    const bool w_smem = smem <= smem_limit(h) && env_int("TK_GRAM_WSMEM", 1) != 0;
+    // new vector through L1 (from 64 modes per GPU on) or staged in shared memory; TK_GRAM_WSMEM = 0 / 1 force
+    const int wsm_env = env_int("TK_GRAM_WSMEM", -1);
+    const bool w_smem = smem <= smem_limit(h) && (wsm_env >= 0 ? wsm_env != 0 : h->dk < 64);
     if (!w_smem) {
         smem = fixed;
         if (monitor > 0 && !h->vscratch.p) TK_TRY(h->vscratch.alloc((size_t)h->dk * h->ldv));
@@ -720,36 +722,6 @@ static int launch_gram(tk_handle* h, int ncols, int base, int nmodes, int monito
     const double bytes = 8.0 * (double)h->n * (double)ncols * nmodes;
     const int U = env_int("TK_GRAM_U", 4);
     TimedScope ts(h, TM_GRAM, bytes, h->stream);
-    // Two grids.  The balanced single-wave form wins when a GPU holds many modes (measured at 1024 modes: 0.95-0.96 of
-    // the HBM peak against 0.93; no tail wave, the new vector re-staged ~4 times per CTA instead of once per 32
-    // columns); with few modes the (chunks, modes) grid is a single wave anyway and its CTAs stage once (256 and 128
-    // modes: 0.82 / 0.75 against 0.75 / 0.63).  A row-sliced grid (nothing staged twice) was measured slower than both
-    // at every size (one warp per column quantises the rounds) and is not kept.  TK_GRAM_MODE = 0 chunks / 1 balanced.
-    const int gm = env_int("TK_GRAM_MODE", -1);
-    const bool balanced = gm == 1 || (gm < 0 && nmodes >= 512);
-    if (w_smem && balanced) {
-        // one wave of resident CTAs, each streaming an equal share of the flat (mode, column) list
-        const size_t smem_b = ((size_t)GRAM_BATCH * GRAM_PSTRIDE + ((h->ncol + 1) & ~1) + (size_t)((h->n + 1) & ~1)) * 8;
-        int per_sm = (threads == 256 && 2 * (smem_b + 2048) <= 227 * 1024) ? 2 : 1;
-        if (env_int("TK_GRAM_PER_SM", 0)) per_sm = env_int("TK_GRAM_PER_SM", 0);
-        const long long total = (long long)ncols * nmodes;
-        const int grid = (int)std::min<long long>(total, (long long)h->sm_count * per_sm);
-#define TK_GRAMB_LAUNCH(UU, TT)                                                                                  \
-        do {                                                                                                     \
-            TK_TRY(allow_smem(gram_row_balanced_kernel<UU, TT>, smem_b));                                        \
-            gram_row_balanced_kernel<UU, TT><<<grid, TT, smem_b, h->stream>>>(h->kp(), ncols, nmodes, base, wpc, \
-                                                                              monitor, h->tickets.p);            \
-        } while (0)
-        if (threads == 512) {
-            if (U == 8) TK_GRAMB_LAUNCH(8, 512); else if (U == 2) TK_GRAMB_LAUNCH(2, 512); else TK_GRAMB_LAUNCH(4, 512);
-        } else {
-            if (U == 8) TK_GRAMB_LAUNCH(8, 256); else if (U == 2) TK_GRAMB_LAUNCH(2, 256); else TK_GRAMB_LAUNCH(4, 256);
-        }
-#undef TK_GRAMB_LAUNCH
-        h->launches++;
-        TK_CUDA(cudaGetLastError());
-        return 0;
-    }
 #define TK_GRAM_LAUNCH(UU, TT)                                                                                   \
     do {                                                                                                         \
         TK_TRY(allow_smem(gram_row_kernel<UU, TT>, smem));                                                       \
@@ -1164,7 +1136,10 @@ static int prepare(tk_handle* h, bool with_schedule) {
     // working vector of the MGS step when it does not fit in shared memory
     const size_t need_gram = ((size_t)32 * GRAM_PSTRIDE + ((h->ncol + 1) & ~1) + (size_t)h->n) * 8;
     const size_t need_mgs = ((size_t)h->ncol + (size_t)h->n) * 8;
-    if ((need_gram > smem_limit(h) || need_mgs > smem_limit(h) || !env_int("TK_GRAM_WSMEM", 1)) && !h->vscratch.p) {
+    // ... or when the Gram-row kernel keeps the new vector in L1 instead of shared memory (launch_gram)
+    const int wsm_env = env_int("TK_GRAM_WSMEM", -1);
+    const bool gram_l1 = wsm_env >= 0 ? wsm_env == 0 : h->dk >= 64;
+    if ((need_gram > smem_limit(h) || need_mgs > smem_limit(h) || gram_l1) && !h->vscratch.p) {
         TK_TRY(h->vscratch.alloc((size_t)h->dk * h->ldv));
         h->cfg_epoch++;
     }

@@ -429,8 +429,13 @@ __device__ __noinline__ void monitor_body(const KrylovParams& p, int s, int newc
 //   g[s][j] = V_s[:,j] . V_s[:,ncols-1],  j = 0..ncols-1
 // The reference forms the whole (k+1)x(k+1) Gram matrix with dgemm at every step in every mode
 // (orthogonal_bases.jl:119); only this row is new, the rest is carried in S[s].
-// grid = (column chunks, modes); a warp streams one column (16-byte loads, 8 in flight per lane)
-// against the new vector staged in shared memory.  HBM-bound: 8*n bytes per column.
+// grid = (column chunks, modes); the warps of a CTA stream two columns at a time (16-byte loads, 8 in flight per
+// lane) against the new vector.  HBM-bound: 8*n bytes per column.
+// The new vector (80 KB at n = 10^4) is read through L1 (w_in_smem = 0: the column streams bypass L1 with
+// .L1::no_allocate, so it stays resident after the first pass) or staged in shared memory first (w_in_smem = 1).
+// L1 is the default from 64 modes per GPU on: a staging phase is a synchronised burst of L2 reads during which the
+// HBM streams of the whole wave stand still (measured, chunks grid: 0.92 -> 0.96 of the HBM peak at 1 024 modes,
+// 0.75 -> 0.79 at 128; with 32 modes the staged form is faster).
 // ------------------------------------------------------------------------------------------
 constexpr int GRAM_PSTRIDE = 16;   // partial sums per column (>= warps per column)
 
@@ -530,122 +535,6 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 2 : 1)) gram_row_ke
     double* v = w_in_smem ? wsm : vscratch + (long long)s * p.ldv;
     monitor_body(p, s, ncols - 1, monitor, hcol, v, scratch);
     if (threadIdx.x == 0) tickets[s] = 0u;
-}
-
-// ------------------------------------------------------------------------------------------
-// Balanced form of the Gram row: the nmodes * ncols columns of one launch are ONE list (mode-major), cut into
-// gridDim.x equal contiguous ranges, one per CTA (grid = resident CTAs of the GPU: a single wave, no tail).  The
-// (chunks, modes) grid above quantises badly when a GPU holds few modes (128 per GPU at d = 1024 on 8 GPUs: 256
-// CTAs on 296 slots) or few columns; here every CTA streams the same number of bytes +- one column for any mode
-// and column count.  A CTA re-stages the new vector when its range crosses into the next mode (L2 hits: the 3-term
-// step has just written it).  tickets[s] counts finished COLUMNS of mode s; the CTA that completes a mode runs the
-// monitor.  Same per-column arithmetic (segments, lanes, association order) as gram_row_kernel: bit-identical g.
-// ------------------------------------------------------------------------------------------
-constexpr int GRAM_BATCH = 32;     // columns per pass of a CTA (size of its partial-sum tile)
-
-template <int U, int THREADS>
-__global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 2 : 1)) gram_row_balanced_kernel(KrylovParams p, int ncols, int nmodes,
-                                                                int mode_base, int wpc, int monitor, unsigned int* tickets) {
-    if (!cta_running(p.status)) return;
-    extern __shared__ double smem[];
-    __shared__ double scratch[32];
-    __shared__ unsigned int my_ticket;
-    const int n = p.n, nq = n >> 1;
-    double* part = smem;                                            // [GRAM_BATCH][GRAM_PSTRIDE]
-    double* hcol = smem + GRAM_BATCH * GRAM_PSTRIDE;                // ncol doubles (MGS fallback)
-    double* wsm = hcol + ((p.ncol + 1) & ~1);
-    const long long total = (long long)nmodes * ncols;
-    long long cur = total * blockIdx.x / gridDim.x;
-    const long long end = total * (blockIdx.x + 1) / gridDim.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = THREADS >> 5;
-    const int seg = warp % wpc, group = warp / wpc, ngroups = nwarp / wpc;
-    const int seglen = (((nq + wpc - 1) / wpc) + 31) & ~31;
-    const int q0 = seg * seglen, q1 = min(nq, q0 + seglen);
-    const double2* w2 = reinterpret_cast<const double2*>(wsm);
-    while (cur < end) {
-        const int sl = (int)(cur / ncols), s = mode_base + sl;
-        const int jfirst = (int)(cur - (long long)sl * ncols);
-        const int jend = (int)min((long long)ncols, jfirst + (end - cur));
-        const double* Vs = p.V + (long long)s * p.vstride;
-        const double* wg = Vs + (long long)(ncols - 1) * p.ldv;
-        __syncthreads();                                            // previous mode's readers of wsm are done
-        {
-            const double2* w2g = reinterpret_cast<const double2*>(wg);
-            double2* s2 = reinterpret_cast<double2*>(wsm);
-            int q = threadIdx.x;
-            for (; q + 3 * THREADS < nq; q += 4 * THREADS) {
-                const double2 t0 = w2g[q], t1 = w2g[q + THREADS], t2 = w2g[q + 2 * THREADS], t3 = w2g[q + 3 * THREADS];
-                s2[q] = t0; s2[q + THREADS] = t1; s2[q + 2 * THREADS] = t2; s2[q + 3 * THREADS] = t3;
-            }
-            for (; q < nq; q += THREADS) s2[q] = w2g[q];
-            if ((n & 1) && threadIdx.x == 0) wsm[n - 1] = wg[n - 1];
-        }
-        __syncthreads();
-        double* g = p.g + (long long)s * p.ncol;
-        for (int c0 = jfirst; c0 < jend; c0 += GRAM_BATCH) {
-            const int c1 = min(jend, c0 + GRAM_BATCH);
-            for (int j = c0 + group; j < c1; j += 2 * ngroups) {
-                const int jb = j + ngroups;
-                const bool two = jb < c1;
-                const double2* ca = reinterpret_cast<const double2*>(Vs + (long long)j * p.ldv);
-                const double2* cb = reinterpret_cast<const double2*>(Vs + (long long)(two ? jb : j) * p.ldv);
-                double a[U], b[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) { a[u] = 0.0; b[u] = 0.0; }
-                int q = q0 + lane;
-                for (; q + 32 * (U - 1) < q1; q += 32 * U) {
-                    double2 x[U], z[U];
-#pragma unroll
-                    for (int u = 0; u < U; ++u) x[u] = ld_stream2(ca + q + 32 * u);
-#pragma unroll
-                    for (int u = 0; u < U; ++u) z[u] = ld_stream2(cb + q + 32 * u);
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const double2 y = w2[q + 32 * u];
-                        a[u] = fma(x[u].x, y.x, a[u]); a[u] = fma(x[u].y, y.y, a[u]);
-                        b[u] = fma(z[u].x, y.x, b[u]); b[u] = fma(z[u].y, y.y, b[u]);
-                    }
-                }
-                for (; q < q1; q += 32) {
-                    const double2 x0 = ld_stream2(ca + q), z0 = ld_stream2(cb + q);
-                    const double2 y0 = w2[q];
-                    a[0] = fma(x0.x, y0.x, a[0]); a[0] = fma(x0.y, y0.y, a[0]);
-                    b[0] = fma(z0.x, y0.x, b[0]); b[0] = fma(z0.y, y0.y, b[0]);
-                }
-                if ((n & 1) && seg == wpc - 1 && lane == 0) {
-                    a[0] = fma(Vs[(long long)j * p.ldv + n - 1], wsm[n - 1], a[0]);
-                    if (two) b[0] = fma(Vs[(long long)jb * p.ldv + n - 1], wsm[n - 1], b[0]);
-                }
-                double sa = 0.0, sb = 0.0;
-#pragma unroll
-                for (int u = 0; u < U; ++u) { sa += a[u]; sb += b[u]; }
-                sa = warp_sum(sa);
-                sb = warp_sum(sb);
-                if (lane == 0) {
-                    part[(j - c0) * GRAM_PSTRIDE + seg] = sa;
-                    if (two) part[(jb - c0) * GRAM_PSTRIDE + seg] = sb;
-                }
-            }
-            __syncthreads();
-            for (int j = c0 + threadIdx.x; j < c1; j += THREADS) {
-                double acc = 0.0;
-                for (int sgi = 0; sgi < wpc; ++sgi) acc += part[(j - c0) * GRAM_PSTRIDE + sgi];
-                g[j] = acc;
-            }
-            __syncthreads();
-        }
-        cur += jend - jfirst;
-        if (monitor < 0) continue;
-        // the CTA that completes the row of this mode folds it into S (and runs the MGS fallback if needed)
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) my_ticket = atomicAdd(tickets + s, (unsigned int)(jend - jfirst));
-        __syncthreads();
-        if (my_ticket + (unsigned int)(jend - jfirst) != (unsigned int)ncols) continue;
-        __threadfence();
-        monitor_body(p, s, ncols - 1, monitor, hcol, wsm, scratch);
-        if (threadIdx.x == 0) tickets[s] = 0u;
-    }
 }
 
 // ------------------------------------------------------------------------------------------
