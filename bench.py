@@ -497,8 +497,8 @@ def run_b200(a):
     peak, peak_kind = measured_peak()
     achieved = top_bytes / (top_ms / 1e3) / 1e9 if top_ms > 0 else 0.0
     tr_ratio, tr_src = measured_traffic_ratio("arnoldi" if kind == 2 else "gram")
-    kname = ("arnoldi_mgs_cluster_kernel (two-pass MGS step of every mode)" if kind == 2
-             else "gram_row_balanced_kernel (orthogonality monitor of the batched Lanczos step)")
+    kname = ("arnoldi_bgs_kernel (two-sweep blocked Gram-Schmidt step of every mode)" if kind == 2
+             else "gram_row_kernel (orthogonality monitor of the batched Lanczos step)")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak" if a.weak else "strong",

@@ -665,7 +665,6 @@ __global__ void __launch_bounds__(THREADS) arnoldi_bgs_kernel(KrylovParams p, in
         }
     };
     auto process = [&](double (&blk)[B][EPT], int c0, int pass) {
-        const int nb = min(B, k - c0);                  // uniform across the CTA
         double h[B];
 #pragma unroll
         for (int q = 0; q < B; ++q) {
@@ -675,23 +674,53 @@ __global__ void __launch_bounds__(THREADS) arnoldi_bgs_kernel(KrylovParams p, in
                 a0 = fma(v[e], blk[q][e], a0);
                 if (e + 1 < EPT) a1 = fma(v[e + 1], blk[q][e + 1], a1);
             }
-            h[q] = warp_sum(a0 + a1);
+            h[q] = a0 + a1;
         }
-        if (lane == 0) {
+        if (B == 4) {
+            // The four sums are reduced TOGETHER: each butterfly step halves the number of values a lane carries
+            // (lanes trade the columns they give up), so the warp stage costs 6 shuffles instead of 20 and ends with the
+            // total of column c in the 8 lanes c*8..c*8+7; the CTA stage reduces the NW warp partials of a column inside
+            // that group of lanes (3 shuffles) and hands the four totals to every lane (4 shuffles).  The sweep is bound
+            // by instruction issue (ncu: one CTA per mode, 8 warps per SM), and the shuffle trees were a third of it.
+            const bool hi = (lane & 16) != 0, h8 = (lane & 8) != 0;
+            double k0 = hi ? h[2] : h[0], k1 = hi ? h[3] : h[1];
+            k0 += __shfl_xor_sync(0xffffffffu, hi ? h[0] : h[2], 16);
+            k1 += __shfl_xor_sync(0xffffffffu, hi ? h[1] : h[3], 16);
+            double kk = h8 ? k1 : k0;
+            kk += __shfl_xor_sync(0xffffffffu, h8 ? k0 : k1, 8);
+            kk += __shfl_xor_sync(0xffffffffu, kk, 4);
+            kk += __shfl_xor_sync(0xffffffffu, kk, 2);
+            kk += __shfl_xor_sync(0xffffffffu, kk, 1);
+            if ((lane & 7) == 0) scr[buf][lane >> 3][warp] = kk;
+            __syncthreads();
+            double t2 = 0.0;
 #pragma unroll
-            for (int q = 0; q < B; ++q) scr[buf][q][warp] = h[q];
+            for (int w = (lane & 7); w < NW; w += 8) t2 += scr[buf][lane >> 3][w];
+            t2 += __shfl_xor_sync(0xffffffffu, t2, 4);
+            t2 += __shfl_xor_sync(0xffffffffu, t2, 2);
+            t2 += __shfl_xor_sync(0xffffffffu, t2, 1);
+#pragma unroll
+            for (int q = 0; q < B; ++q) h[q] = __shfl_sync(0xffffffffu, t2, q * 8);
+        } else {
+#pragma unroll
+            for (int q = 0; q < B; ++q) h[q] = warp_sum(h[q]);
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < B; ++q) scr[buf][q][warp] = h[q];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < B; ++q) h[q] = warp_sum((lane < NW) ? scr[buf][q][lane] : 0.0);
         }
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < B; ++q) h[q] = warp_sum((lane < NW) ? scr[buf][q][lane] : 0.0);
         buf ^= 1;
+        // columns past the k-th are clamped copies of it: projecting with h = 0 leaves the working vector unchanged,
+        // so the tail block needs no branch
 #pragma unroll
         for (int q = 0; q < B; ++q) {
-            if (q < nb) {
-                if (tid == 0) hcol[c0 + q] = pass ? hcol[c0 + q] + h[q] : h[q];
+            if (c0 + q >= k) h[q] = 0.0;
+            else if (tid == 0) hcol[c0 + q] = pass ? hcol[c0 + q] + h[q] : h[q];
 #pragma unroll
-                for (int e = 0; e < EPT; ++e) v[e] = fma(-h[q], blk[q][e], v[e]);
-            }
+            for (int e = 0; e < EPT; ++e) v[e] = fma(-h[q], blk[q][e], v[e]);
         }
     };
     for (int pass = 0; pass < 2; ++pass) {
