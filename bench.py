@@ -78,7 +78,7 @@ def workload_name(a):
     c = CONFIGS[a.config]
     tag = a.config if (a.d, a.n, a.nmax, a.variant) == (c["d"], c["n"], c["nmax"], c["variant"]) and not a.t_override else a.config + "-variant"
     var = {"reorth": "TensorLanczosReorth", "lanczos": "TensorLanczos", "arnoldi": "TensorArnoldi"}[a.variant]
-    extra = f" t={a.t_override}" if a.t_override else ""
+    extra = f" t=min({a.t_override},tabulated)" if a.t_override else ""
     return (f"{tag} d={a.d} n={a.n} {a.cls} {var} nmax={a.nmax} tol={a.tol:g}{extra} fixed-iterations "
             f"{'per-mode H_s' if a.per_mode else 'reference H_1'}")
 
@@ -333,7 +333,12 @@ def run_b200(a):
             # the rank sweep of config 5: the coefficient file of rank t in the table row of every iteration's kappa
             for k in range(2, nmax + 1):
                 lmin, lmax = tk.extreme_eigvals(A1, d, k, instance, cls)
-                om, al, _ = tk.sym_rank_coefficients(lmax * (1.0 / lmin), a.t_override)
+                for t in range(a.t_override, 0, -1):       # rows of small condition number are not tabulated up to rank 63
+                    try:
+                        om, al, _ = tk.sym_rank_coefficients(lmax * (1.0 / lmin), t)
+                        break
+                    except tk.TKError:
+                        continue
                 s.set_schedule_entry(k, lmin, al, om)
         else:
             s.set_schedule(A1, a.tol if tol is None else tol)

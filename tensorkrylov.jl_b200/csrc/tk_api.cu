@@ -776,7 +776,7 @@ static int launch_arnoldi(tk_handle* h, int k) {
         if (h->n <= 128 * 4) TK_BGS_LAUNCH(4, 128, 4);
         if (h->n <= 256 * 4) TK_BGS_LAUNCH(4, 256, 4);
         // one CTA per mode leaves the SM with few warps: more, thinner threads hide the issue latency of the sweep
-        const int bth = env_int("TK_BGS_THREADS", 512);
+        const int bth = env_int("TK_BGS_THREADS", 256);
         if (h->n <= 1024 * 2 && bth == 1024) TK_BGS_LAUNCH(2, 1024, 4);
         if (h->n <= 512 * 4 && bth >= 512) TK_BGS_LAUNCH(4, 512, 4);
         if (h->n <= 256 * 8) TK_BGS_LAUNCH(8, 256, 4);

@@ -487,9 +487,10 @@ def test_solve_matches_reference_history_laplace_more_modes(tk, gpu, d):
     assert np.max(np.abs(cd.relative_residual_norm[k - 1] - rr[k - 1]) / rr[k - 1]) < 1e-7
 
 
-def test_solve_converges_and_returns_kruskal(tk, orc, tables, gpu):
-    """A configuration that reaches its tolerance (large d, tol 1e-4): status, iteration count, ConvergenceData
-    conventions and the Kruskal solution x = (lambda, V_s Y_s) all match the oracle."""
+def test_solve_that_stops_at_nmax_returns_nothing(tk, orc, tables, gpu):
+    """d = 64, n = 1000, tol 1e-4, nmax = 40 does NOT reach its tolerance (neither here nor in the oracle): status NMAX,
+    "No convergence", no Kruskal tensor, histories equal.  (The converged exit, with the oracle's x, is
+    tests/test_gpu_baseline_sizes.py::test_converged_exit_returns_the_oracles_kruskal_tensor.)"""
     d, n, nmax, tol = 64, 1000, 40, 1e-4
     b = np.random.default_rng(12345).random(n)
     A = tk.KroneckerMatrix.gallery(tk.SymInstance, d, n, tk.Laplace)
@@ -499,16 +500,9 @@ def test_solve_converges_and_returns_kruskal(tk, orc, tables, gpu):
     Ao = orc.assemble_matrix(n, orc.LAPLACE)
     S = orc.tensorkrylov([Ao] * d, orc.normalize_rhs([b] * d), tol, nmax, orc.LANCZOS_REORTH, orc.SYM, orc.LAPLACE,
                          tables, fast_solve=True)
-    assert cd.status == S.status
-    if S.status == orc.ST_CONVERGED:
-        assert x is not None and cd.term_k == S.k and cd.niterations == nmax
-        lam, fm = S.x
-        assert rel(x.lambda_, lam) < 1e-13
-        for s in (0, d // 2, d - 1):
-            assert rel(x.fmat[s], fm[s]) < 1e-9
-    elif S.status == orc.ST_BREAKDOWN:
-        assert x is None and cd.niterations == S.niterations and len(cd.relative_residual_norm) == S.niterations
-    kk = np.arange(2, min(S.k, cd.term_k))
+    assert S.status == orc.ST_NMAX
+    assert cd.status == tk.TK_NMAX and x is None and cd.term_k == nmax and cd.niterations == nmax
+    kk = np.arange(2, nmax + 1)
     assert_relres_close(cd.relative_residual_norm[kk - 1], S.relres[kk - 1])
 
 
