@@ -801,34 +801,9 @@ static int launch_arnoldi(tk_handle* h, int k) {
     return 0;
 }
 
-// One CTA per mode doing 3-term step + Gram row + monitor (lanczos_fused_step_kernel): when this GPU holds about one
-// mode per SM.  Returns 1 when the configuration is not eligible.
-static int launch_fused_step(tk_handle* h, int k, int nmon, int monitor) {
-    const int mode = env_int("TK_FUSED_STEP", -1);
-    if (mode == 0) return 1;
-    if (h->dk > h->sm_count || (mode < 0 && h->dk < env_int("TK_FUSED_MIN", 96))) return 1;
-    const size_t np = ((size_t)h->n + 1) & ~(size_t)1;
-    const size_t smem = (2 * np + 32 * GRAM_PSTRIDE + (((size_t)h->ncol + 1) & ~(size_t)1)) * 8;
-    if (smem > 220 * 1024 || h->n < 64) return 1;
-    auto kernel = lanczos_fused_step_kernel<512>;
-    TK_TRY(allow_smem(kernel, smem));
-    // algorithmic bytes: v_k, v_{k-1}, b read, v_{k+1} written, columns 1..k-1 read (the two newest stay on chip)
-    const double bytes = (8.0 * (k + 3) + op_bytes_per_row(h)) * (double)h->n * h->dk;
-    TimedScope ts(h, TM_GRAM, bytes, h->stream);
-    kernel<<<h->dk, 512, smem, h->stream>>>(h->kp(), k, monitor, nmon);
-    h->launches++;
-    TK_CUDA(cudaGetLastError());
-    return 0;
-}
-
 // orthonormalize!(decomp, k) for every local mode + update_rhs!   (orthogonal_bases.jl:162-180, utils.jl:466-476)
 static int enqueue_step_bases(tk_handle* h, int k) {
     const int mode0 = (h->first == 0 && h->dl > 0) ? 1 : 0;
-    if (h->variant != TK_ARNOLDI) {
-        const int rc = launch_fused_step(h, k, h->variant == TK_LANCZOS_REORTH ? h->dk : mode0,
-                                         h->variant == TK_LANCZOS_REORTH ? 1 : 0);
-        if (rc != 1) return rc;
-    }
     if (h->variant == TK_ARNOLDI) {
         TK_TRY(launch_arnoldi(h, k));
         TK_TRY(launch_gram(h, k + 1, 0, mode0, 0));

@@ -538,162 +538,6 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 2 : 1)) gram_row_ke
 }
 
 // ------------------------------------------------------------------------------------------
-// Fused Lanczos step for GPUs that hold about one mode per SM (128 modes per GPU at d = 1024 on 8 GPUs): ONE CTA per
-// mode does the 3-term step, the Gram row of the new vector and the monitor in one launch.  With so few modes the two
-// separate kernels are latency-bound -- the 3-term step takes 19 us for 6 us of traffic, the Gram row spends 14 of
-// its 65 us ramping up, staging and draining -- and everything the Gram row needs first is what the 3-term step has
-// just produced.  Here v_k and v_{k-1} are loaded into shared memory once (L2 hits: the previous launch wrote them),
-// the three passes of the recurrence run out of shared memory (u overwrites v_{k-1} in place and ends up holding
-// v_{k+1}), and the Gram row streams columns 1..k-1 from HBM against the new vector in shared memory while
-// g_k = v_k.v_{k+1} and g_{k+1} = v_{k+1}.v_{k+1} come from shared memory: two columns, the staging pass and one
-// launch less per iteration, and no cluster barriers.  Same arithmetic per row as lanczos_ttr_kernel; the reduction
-// trees differ (one CTA instead of a cluster), so results agree with the two-kernel path to rounding, not bit for bit.
-// Not used with many modes per GPU (several waves: measured -35 % at 1 024 modes in round 1) or with few
-// (32 modes would leave 116 SMs idle).
-// ------------------------------------------------------------------------------------------
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 1) lanczos_fused_step_kernel(KrylovParams p, int k, int monitor /* 0 / 1 = reorth */,
-                                                                        int gram_modes /* modes [0, gram_modes) get a Gram row */) {
-    if (!cta_running(p.status)) return;
-    extern __shared__ __align__(16) double smem[];
-    __shared__ double scratch[64];
-    const int s = blockIdx.x, n = p.n, tid = threadIdx.x;
-    const int np = (n + 1) & ~1;
-    double* vks = smem;                 // v_k
-    double* us = smem + np;             // v_{k-1}, then u, then v^, then v_{k+1}
-    double* part = us + np;             // [32][GRAM_PSTRIDE] partial sums of a batch of columns
-    double* hcol = part + 32 * GRAM_PSTRIDE;
-    const OpDesc& op = p.ops[p.mode_op[s]];
-    double* Vs = p.V + (long long)s * p.vstride;
-    const double* vk = Vs + (long long)(k - 1) * p.ldv;
-    const double* vkm1 = (k >= 2) ? Vs + (long long)(k - 2) * p.ldv : nullptr;
-    const double* b = p.b + (long long)s * p.ldv;
-    double* vnew = Vs + (long long)k * p.ldv;
-    double* T = p.T + (long long)s * 3 * p.ncol;
-    const double beta_prev = (k >= 2) ? T[2 * p.ncol + (k - 2)] : 0.0;  // H[k-1,k]  (decompositions.jl:78)
-    // ---- stage v_k and v_{k-1} (16-byte loads; columns are padded to a multiple of 16 doubles)
-    {
-        const double2* a2 = reinterpret_cast<const double2*>(vk);
-        const double2* c2 = reinterpret_cast<const double2*>(vkm1);
-        double2* sa = reinterpret_cast<double2*>(vks);
-        double2* sc = reinterpret_cast<double2*>(us);
-        const int nq = np >> 1;
-        for (int q = tid; q < nq; q += THREADS) {
-            sa[q] = a2[q];
-            sc[q] = vkm1 ? c2[q] : make_double2(0.0, 0.0);
-        }
-    }
-    __syncthreads();
-    // ---- u = A v_k - beta_{k-1} v_{k-1};  alpha = u . v_k          (orthogonal_bases.jl:45-50)
-    double acc = 0.0;
-    for (int i = tid; i < n; i += THREADS) {
-        double ui = apply_row(op, vks, i, n);
-        ui -= beta_prev * us[i];
-        acc = fma(ui, vks[i], acc);
-        us[i] = ui;                      // row i of v_{k-1} is only read by this thread: in place
-    }
-    const double alpha = block_sum(acc, scratch);
-    // ---- v^ = u - alpha v_k;  beta = ||v^||;  v^.b                  (:53-56, utils.jl:466-476)
-    double accb = 0.0;
-    acc = 0.0;
-    for (int i = tid; i < n; i += THREADS) {
-        const double w = us[i] - alpha * vks[i];
-        us[i] = w;
-        acc = fma(w, w, acc);
-        accb = fma(w, __ldg(b + i), accb);
-    }
-    block_sum2(acc, accb, scratch);
-    const double beta = sqrt(acc);
-    const double inv = (beta == 0.0) ? 0.0 : 1.0 / beta;
-    // ---- v_{k+1} = v^ / beta (zeros if beta == 0), kept in shared memory for the Gram row      (:59)
-    double gkk = 0.0, gk1 = 0.0;
-    for (int i = tid; i < n; i += THREADS) {
-        const double x = inv * us[i];
-        us[i] = x;
-        vnew[i] = x;
-        gkk = fma(x, x, gkk);            // g_{k+1} = v_{k+1} . v_{k+1}
-        gk1 = fma(vks[i], x, gk1);       // g_k     = v_k . v_{k+1}
-    }
-    if (tid == 0) {
-        T[k - 1] = alpha;                   // H[k,k]
-        T[p.ncol + (k - 1)] = beta;         // H[k+1,k]
-        T[2 * p.ncol + (k - 1)] = beta;     // H[k,k+1]   update_subdiagonals!, decompositions.jl:180-186
-        p.bt[(long long)s * p.ncol + k] = inv * accb;
-    }
-    if (s >= gram_modes) return;            // TensorLanczos: only mode 1 keeps the orthogonality history (:103)
-    block_sum2(gkk, gk1, scratch);          // also orders the writes of v_{k+1} before the reads below
-    double* g = p.g + (long long)s * p.ncol;
-    if (tid == 0) { g[k] = gkk; g[k - 1] = gk1; }
-    // ---- Gram row against columns 1..k-1 (0-based 0..k-2) from HBM, the new vector from shared memory
-    const int ncols = k - 1;
-    const int nq = n >> 1;
-    const int lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = THREADS / 32;
-    constexpr int WPC = NW < GRAM_PSTRIDE ? NW : GRAM_PSTRIDE;     // warps per column (all of them, at most 16)
-    constexpr int NG = NW / WPC;                                    // columns processed side by side
-    const int seg = warp % WPC, group = warp / WPC;
-    const int seglen = (((nq + WPC - 1) / WPC) + 31) & ~31;
-    const int q0 = seg * seglen, q1 = min(nq, q0 + seglen);
-    const double2* w2 = reinterpret_cast<const double2*>(us);
-    constexpr int U = 4;
-    for (int c0 = 0; c0 < ncols; c0 += 32) {
-        const int c1 = min(ncols, c0 + 32);
-        for (int j = c0 + group; j < c1; j += 2 * NG) {
-            const int jb = j + NG;
-            const bool two = jb < c1;
-            const double2* ca = reinterpret_cast<const double2*>(Vs + (long long)j * p.ldv);
-            const double2* cb = reinterpret_cast<const double2*>(Vs + (long long)(two ? jb : j) * p.ldv);
-            double a[U], bb[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) { a[u] = 0.0; bb[u] = 0.0; }
-            int q = q0 + lane;
-            for (; q + 32 * (U - 1) < q1; q += 32 * U) {
-                double2 x[U], z[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) x[u] = ld_stream2(ca + q + 32 * u);
-#pragma unroll
-                for (int u = 0; u < U; ++u) z[u] = ld_stream2(cb + q + 32 * u);
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const double2 y = w2[q + 32 * u];
-                    a[u] = fma(x[u].x, y.x, a[u]); a[u] = fma(x[u].y, y.y, a[u]);
-                    bb[u] = fma(z[u].x, y.x, bb[u]); bb[u] = fma(z[u].y, y.y, bb[u]);
-                }
-            }
-            for (; q < q1; q += 32) {
-                const double2 x0 = ld_stream2(ca + q), z0 = ld_stream2(cb + q);
-                const double2 y0 = w2[q];
-                a[0] = fma(x0.x, y0.x, a[0]); a[0] = fma(x0.y, y0.y, a[0]);
-                bb[0] = fma(z0.x, y0.x, bb[0]); bb[0] = fma(z0.y, y0.y, bb[0]);
-            }
-            if ((n & 1) && seg == WPC - 1 && lane == 0) {
-                a[0] = fma(Vs[(long long)j * p.ldv + n - 1], us[n - 1], a[0]);
-                if (two) bb[0] = fma(Vs[(long long)jb * p.ldv + n - 1], us[n - 1], bb[0]);
-            }
-            double sa = 0.0, sb = 0.0;
-#pragma unroll
-            for (int u = 0; u < U; ++u) { sa += a[u]; sb += bb[u]; }
-            sa = warp_sum(sa);
-            sb = warp_sum(sb);
-            if (lane == 0) {
-                part[(j - c0) * GRAM_PSTRIDE + seg] = sa;
-                if (two) part[(jb - c0) * GRAM_PSTRIDE + seg] = sb;
-            }
-        }
-        __syncthreads();
-        for (int j = c0 + tid; j < c1; j += THREADS) {
-            double t = 0.0;
-            for (int sgi = 0; sgi < WPC; ++sgi) t += part[(j - c0) * GRAM_PSTRIDE + sgi];
-            g[j] = t;
-        }
-        __syncthreads();
-    }
-    __threadfence();
-    __syncthreads();
-    monitor_body(p, s, k, monitor, hcol, us, scratch);
-}
-
-// ------------------------------------------------------------------------------------------
 // Register-resident Arnoldi step: same two-pass MGS in the reference's order, but the working vector lives in
 // registers (EPT rows per thread), each basis column is fetched ONCE per pass (the dot and the update use the same
 // registers), the next PD columns are already in flight while the current one is being reduced, and the block reduction

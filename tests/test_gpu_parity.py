@@ -708,51 +708,3 @@ def test_bulk_copy_ttr_kernel_is_bit_identical_to_the_plain_kernel(tk, orc, gpu,
         assert np.array_equal(Ha, Hb)
         assert np.array_equal(Va, Vb)
         assert np.array_equal(ba, bb)
-
-
-@pytest.mark.parametrize("variant_name", ["reorth", "lanczos"])
-def test_fused_step_kernel_matches_the_two_kernel_path(tk, orc, tables, gpu, monkeypatch, variant_name):
-    """lanczos_fused_step_kernel (one CTA per mode: 3-term step + Gram row + monitor, chosen when a GPU holds about
-    one mode per SM) against the two-kernel path and against the oracle: coefficients, b~ and residual terms to 1e-11,
-    the orthogonality history to rounding, through dozens of MGS fallbacks (clustered spectrum j^2/n^2 given as a
-    sparse diagonal operator under the RandSPD spectral rule)."""
-    variant = tk.TensorLanczosReorth if variant_name == "reorth" else tk.TensorLanczos
-    ovariant = orc.LANCZOS_REORTH if variant_name == "reorth" else orc.LANCZOS
-    cases = [(tk.assemble_matrix(1001, tk.Laplace), tk.Laplace, orc.LAPLACE, 7, 1001, 40)]      # odd n
-    if variant_name == "reorth":
-        ev = (np.arange(1, 201) / 200.0) ** 2
-        cases.append((sp.diags(ev).tocsc(), tk.RandSPD, orc.RANDSPD, 5, 200, 120))
-    for A, cls, ocls, d, n, nmax in cases:
-        b = np.random.default_rng(11).random(n)
-        b /= np.linalg.norm(b)
-        runs = {}
-        for fused in ("0", "1"):
-            monkeypatch.setenv("TK_FUSED_STEP", fused)
-            slv = make_solver(tk, [A] * d, [b] * d, nmax, variant, tk.SymInstance, cls,
-                              flags=tk.TK_FLAG_REFERENCE_H1 | tk.TK_FLAG_FIXED_ITERATIONS, tol=1e-9)
-            res = slv.solve(1e-9)
-            runs[fused] = (res, slv.detail(), slv.get_H(0), slv.get_bt(0), slv.orth_state(0)[1], slv.launch_count())
-            slv.close()
-        monkeypatch.delenv("TK_FUSED_STEP")
-        (ra, da, Ha, ba, fa, la), (rb, db, Hb, bb_, fb, lb) = runs["0"], runs["1"]
-        assert lb < la                                       # one launch per iteration less
-        if fa == 0 and fb == 0:
-            # no fallback: the two paths differ by summation order only
-            assert np.abs(Ha - Hb).max() <= 1e-13 * np.abs(Ha).max()
-            assert np.abs(ba - bb_).max() <= 1e-12 * np.abs(ba).max()
-            for key in ("hy2", "hyb", "bb"):
-                assert np.max(np.abs(da[key] - db[key]) / np.abs(da[key])) < RTOL
-            assert_relres_close(ra["relres"][1:], rb["relres"][1:])
-        else:
-            assert fa > 10 and abs(fa - fb) <= 2                 # the trigger compares a noise-level loss with sqrt(eps)
-            kk = np.arange(2, 50)
-            assert_relres_close(ra["relres"][kk - 1], rb["relres"][kk - 1])
-            assert rb["orth"][1:].max() < 2e-8
-        # and the fused path against the oracle
-        Ao = A.tocsr() if sp.issparse(A) else A
-        S = orc.OracleSolve([Ao] * d, [b] * d, 1e-9, min(nmax, 40), ovariant, orc.SYM, ocls, tables, ignore_breakdown=True)
-        S.run()
-        kk = np.arange(2, min(nmax, 40) + 1)
-        assert_relres_close(rb["relres"][kk - 1], S.relres[kk - 1])
-        m = min(nmax, 40)
-        assert np.abs(Hb[:m, : m - 1] - S.H[0][:m, : m - 1]).max() <= 1e-11 * np.abs(S.H[0]).max()
