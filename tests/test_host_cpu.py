@@ -351,3 +351,37 @@ def test_minor_extremes_match_lapack(tk):
     out = np.zeros(8)
     assert lib.tk_minor_extremes(capi.dptr(np.asfortranarray(R)), 3, 3, 1, capi.dptr(out)) == -7
     assert b"complex" in lib.tk_last_error()
+
+
+def test_committed_r02_launch_list_matches_its_summary():
+    """profiles/ (round 2): one whole warm solve is 383 launches -- 6 per iteration (3-term step, Gram row + monitor,
+    bisection, QL fallback check, assembly + Gram blocks, combine + exchange + finalize) plus reset, init, the first
+    Gram row and step 1 -- and the per-kernel totals in the summary are the sums of its rows."""
+    import collections, csv, re
+    rows = [r for r in csv.reader(open(os.path.join(ROOT, "profiles", "r02_ncu_launches_bench_n1.csv"))) if r and r[0].isdigit()]
+    assert len(rows) == 383
+    tot, cnt = collections.Counter(), collections.Counter()
+    for r in rows:
+        name = re.sub(r"<.*$", "", re.sub(r"\(.*$", "", r[4]).replace("void ", "").replace("tk::", "").strip())
+        tot[name] += float(r[-1].replace(",", "")) / (1e6 if r[-2] in ("ns", "nsecond") else 1e3)
+        cnt[name] += 1
+    assert cnt["gram_row_kernel"] == 65 and cnt["lanczos_ttr_bulk_kernel"] == 64 and cnt["combine_chunk_kernel"] == 63
+    assert cnt["reset_kernel"] == 1 and "finalize_kernel" not in cnt      # the final merge runs inside the combine kernel
+    summary = open(os.path.join(ROOT, "profiles", "r02_ncu_launch_summary.txt")).read()
+    gram = float(re.search(r"^gram_row_kernel\s+(\d+)\s+([\d.]+)", summary, re.M).group(2))
+    assert abs(gram - tot["gram_row_kernel"]) < 0.01
+    assert tot["gram_row_kernel"] > tot["lanczos_ttr_bulk_kernel"] > 0
+
+
+def test_committed_bench_lines_carry_the_contract_keys():
+    """profiles/r02_bench_n{1,2,4,8}: one JSON line each with the contract's keys, parity green at every N."""
+    import json
+    for name, n in (("r02_bench_n1.json", 1), ("r02_bench_n2_2gpu_box.json", 2), ("r02_bench_n4.json", 4), ("r02_bench_n8.json", 8)):
+        d = json.load(open(os.path.join(ROOT, "profiles", name)))
+        assert d["metric"] == "krylov_iters_per_s" and d["n_gpus"] == n and d["dtype"] == "f64" and d["value"] > 0
+        assert d["roofline"]["bound"] == "hbm" and 0 < d["roofline"]["frac"] < 1.1 and d["gpu_launches"] > 0
+        assert d["parity"]["checked"] and d["parity"]["ok"]
+        assert "workload" in d["config"] and d["clocks"]["sm_mhz"] > 0
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_n1.json")))
+    assert d["cpu_baseline"]["kind"] == "port" and "nothing scaled" in d["cpu_baseline"]["sample"]
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["time_to_tol"]["with_solution_ms"] > d["time_to_tol"]["device_ms"]
