@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges cost nothing unless a profiler is attached
 
 #include <algorithm>
 #include <chrono>
@@ -174,6 +175,12 @@ struct DevBuf {
         }
         return 0;
     }
+};
+
+// NVTX range over a phase of the host-side driver (solve, segment, graph recording, solution fetch)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
 };
 
 struct HostOp {
@@ -1062,6 +1069,7 @@ static int enqueue_residual(tk_handle* h, int k) {
 // ranks must agree on the path, so the outcome is voted on (a second all-gather); if any rank could not map a
 // peer the solve keeps NCCL's all-gather.  Collective: called by all ranks from the first tk_solve / tk_compress.
 static int setup_peer_exchange(tk_handle* h) {
+    NvtxRange range("tk peer exchange setup");
     h->px_ready = false;
     if (h->world > PX_MAX || !env_int("TK_PEER", 1)) return 0;
     const long long slot = (h->pstride_max + 1) & ~1LL;
@@ -1283,8 +1291,10 @@ static void plan_segments(tk_handle* h) {
 
 static int launch_segment(tk_handle* h, int idx, bool graph) {
     tk_handle::Segment& sg = h->segs[idx];
+    NvtxRange range("tk segment");
     if (!graph) return enqueue_segment(h, idx);
     if (!sg.exec || sg.epoch != h->cfg_epoch) {
+        NvtxRange rec("tk record graph");
         const auto t0 = std::chrono::steady_clock::now();
         if (sg.exec) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; }
         const long long before = h->launches;
@@ -1823,6 +1833,7 @@ int tk_residual(tk_handle* h, int32_t k, double tol, double* out8) {
 int tk_solve(tk_handle* h, double tol, int32_t* status, int64_t* niter, int32_t* term_k, double* relres, double* projres,
              double* orth) {
     if (!h) return set_error(TK_EINVAL, "null handle");
+    NvtxRange range("tk_solve");
     TK_CUDA(cudaSetDevice(h->device));
     const unsigned long long epoch_before = h->cfg_epoch;
     TK_TRY(prepare(h, true));
@@ -1941,6 +1952,7 @@ static bool host_pointer_is_pinned(const void* p) {
 // through two pinned staging buffers and a host copy.
 static int solution_to_host(tk_handle* h, int k, int t, int tld, int m0, int nm, double* fmat) {
     if (nm <= 0) return 0;
+    NvtxRange range("tk solution to host");
     tk_resources* r = h->res;
     const size_t per_mode = (size_t)h->n * t;                      // doubles
     const size_t chunk_bytes_target = (size_t)std::max(1, env_int("TK_SOL_CHUNK_MB", 32)) << 20;

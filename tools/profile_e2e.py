@@ -1,11 +1,11 @@
 import os, sys, time
 import numpy as np
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as entry
 tk = entry.load_package()
 import ctypes as C
 lib = tk._capi.lib
-d, n, nmax = 1024, 10000, 64
+d, n, nmax = (int(sys.argv[1]) if len(sys.argv) > 1 else 1024), 10000, 64
 A1 = tk.assemble_matrix(n, tk.Laplace)
 b = np.random.default_rng(12345).random(n); b /= np.linalg.norm(b)
 flags = tk.TK_FLAG_FIXED_ITERATIONS | tk.TK_FLAG_REFERENCE_H1
