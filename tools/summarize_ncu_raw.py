@@ -32,7 +32,7 @@ def short(name):
 
 
 def main():
-    print("# from `ncu --set full --clock-control none` captures (tools/r2_call2.sh); one row per profiled launch")
+    print("# from `ncu --set full --clock-control none` captures (tools/run_evidence_1gpu.sh); one row per profiled launch")
     hdrline = f"{'kernel':<46} " + " ".join(f"{lab:>10}" for _, lab, _ in KEEP)
     for path in sys.argv[1:]:
         rows = list(csv.reader(open(path)))
