@@ -177,6 +177,20 @@ struct DevBuf {
     }
 };
 
+// Peer-exchange buffers of one (communicator, slot size): receive buffer and flags of this rank plus the mapped views of
+// every peer's.  Setting them up is collective (two all-gathers, IPC export / open), so they belong to the process,
+// not to a handle: a solver created later on the same communicator with the same slot size borrows them (a drop-in
+// caller creates a handle per solve).  The flag values only ever grow, across handles too: `epoch` is the running
+// base, advanced by nmax + 2 per solve -- every rank runs the same sequence of solves, so all ranks agree on it.
+struct ExchangeCtx {
+    DevBuf<double> recv;
+    DevBuf<unsigned long long> flags;
+    PeerExchange px;
+    bool ready = false;
+    long long epoch = 0;
+};
+static std::map<std::pair<std::string, long long>, std::unique_ptr<ExchangeCtx>> g_exchange;
+
 // NVTX range over a phase of the host-side driver (solve, segment, graph recording, solution fetch)
 struct NvtxRange {
     explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
@@ -325,8 +339,8 @@ struct tk_handle {
     // peer exchange of the merged partials (world > 1): receive buffer + flags of this rank, peers' mapped views
     PeerExchange px;
     bool px_ready = false;
-    DevBuf<double> px_recv;
-    DevBuf<unsigned long long> px_flags;
+    ExchangeCtx* xc = nullptr;           // process-level buffers behind px (not owned)
+    std::string comm_key;                // the NCCL unique id this handle's communicator was made from
 
     // Krylov state
     DevBuf<double> V, b, T, Hd, bt, g, S, orthS, bnorm2, vscratch;
@@ -1071,16 +1085,31 @@ static int enqueue_residual(tk_handle* h, int k) {
 static int setup_peer_exchange(tk_handle* h) {
     NvtxRange range("tk peer exchange setup");
     h->px_ready = false;
+    h->xc = nullptr;
     if (h->world > PX_MAX || !env_int("TK_PEER", 1)) return 0;
     const long long slot = (h->pstride_max + 1) & ~1LL;
-    TK_TRY(h->px_recv.alloc((size_t)2 * h->world * slot));
-    TK_TRY(h->px_flags.alloc((size_t)h->world));
+    const auto key = std::make_pair(h->comm_key, slot);
+    {
+        std::lock_guard<std::mutex> lock(g_mutex);
+        auto it = g_exchange.find(key);
+        if (it != g_exchange.end()) {        // set up by an earlier handle (on every rank alike): nothing collective left
+            h->xc = it->second.get();
+            h->px = h->xc->px;
+            h->px_ready = h->xc->ready;
+            if (!h->px_ready && env_int("TK_PEER", 1) == 2)
+                return set_error(TK_ECUDA, "peer mapping of the exchange buffers failed (TK_PEER=2 forbids the NCCL fallback)");
+            return 0;
+        }
+    }
+    std::unique_ptr<ExchangeCtx> xc(new ExchangeCtx());
+    TK_TRY(xc->recv.alloc((size_t)2 * h->world * slot));
+    TK_TRY(xc->flags.alloc((size_t)h->world));
     struct Rec { cudaIpcMemHandle_t recv, flag; int ok; int pad[15]; };
     static_assert(sizeof(Rec) % 8 == 0, "record is shipped as doubles");
     Rec mine;
     std::memset(&mine, 0, sizeof(mine));
-    mine.ok = cudaIpcGetMemHandle(&mine.recv, h->px_recv.p) == cudaSuccess &&
-              cudaIpcGetMemHandle(&mine.flag, h->px_flags.p) == cudaSuccess;
+    mine.ok = cudaIpcGetMemHandle(&mine.recv, xc->recv.p) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.flag, xc->flags.p) == cudaSuccess;
     cudaGetLastError();
     DevBuf<double> ex;
     const size_t rd = sizeof(Rec) / 8;
@@ -1099,19 +1128,18 @@ static int setup_peer_exchange(tk_handle* h) {
     px.world = h->world; px.rank = h->rank; px.slot_stride = slot;
     bool ok = true;
     for (int r = 0; r < h->world; ++r) ok = ok && all[r].ok;
-    // Mappings are kept for the life of the process, keyed by the exported handle: a peer whose next solver gets
-    // the same cached device blocks exports the same handles, and opening one costs ~0.1 ms (14 per rank at N = 8).
+    // Mappings are kept for the life of the process, keyed by the exported handle (opening one costs ~0.1 ms).
     auto open_cached = [&](const cudaIpcMemHandle_t& mh, void** out) -> bool {
-        const std::string key(reinterpret_cast<const char*>(&mh), sizeof(mh));
+        const std::string k2(reinterpret_cast<const char*>(&mh), sizeof(mh));
         std::lock_guard<std::mutex> lock(g_mutex);
-        auto it = g_ipc_open.find(key);
+        auto it = g_ipc_open.find(k2);
         if (it != g_ipc_open.end()) { *out = it->second; return true; }
         if (cudaIpcOpenMemHandle(out, mh, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) return false;
-        g_ipc_open[key] = *out;
+        g_ipc_open[k2] = *out;
         return true;
     };
     for (int r = 0; r < h->world && ok; ++r) {
-        if (r == h->rank) { px.recv[r] = h->px_recv.p; px.flag[r] = h->px_flags.p; continue; }
+        if (r == h->rank) { px.recv[r] = xc->recv.p; px.flag[r] = xc->flags.p; continue; }
         void *pr = nullptr, *pf = nullptr;
         if (!open_cached(all[r].recv, &pr) || !open_cached(all[r].flag, &pf)) { ok = false; break; }
         px.recv[r] = static_cast<double*>(pr);
@@ -1121,13 +1149,18 @@ static int setup_peer_exchange(tk_handle* h) {
     mine.ok = ok ? 1 : 0;
     TK_TRY(gather());                       // vote: also orders every rank's mapping before anybody's first store
     for (int r = 0; r < h->world; ++r) ok = ok && all[r].ok;
-    if (!ok) {
-        cudaGetLastError();
-        if (env_int("TK_PEER", 1) == 2) return set_error(TK_ECUDA, "peer mapping of the exchange buffers failed (TK_PEER=2 forbids the NCCL fallback)");
-        return 0;
-    }
+    cudaGetLastError();
+    xc->px = px;
+    xc->ready = ok;
     h->px = px;
-    h->px_ready = true;
+    h->px_ready = ok;
+    {
+        std::lock_guard<std::mutex> lock(g_mutex);
+        h->xc = xc.get();
+        g_exchange[key] = std::move(xc);
+    }
+    if (!ok && env_int("TK_PEER", 1) == 2)
+        return set_error(TK_ECUDA, "peer mapping of the exchange buffers failed (TK_PEER=2 forbids the NCCL fallback)");
     return 0;
 }
 
@@ -1158,7 +1191,12 @@ static int prepare(tk_handle* h, bool with_schedule) {
 static void arm_solve(tk_handle* h, double tol) {
     h->solve_count++;
     h->hctl->tol = tol;
-    h->hctl->epoch = h->solve_count * (long long)(h->nmax + 2);
+    if (h->xc && h->px_ready) {            // flags of the shared exchange buffers grow across handles
+        h->xc->epoch += h->nmax + 2;
+        h->hctl->epoch = h->xc->epoch;
+    } else {
+        h->hctl->epoch = h->solve_count * (long long)(h->nmax + 2);
+    }
     h->hctl->term_k = 0;
     h->hctl->niter = h->nmax;
     *reinterpret_cast<volatile int*>(&h->hctl->status) = ST_RUNNING;
@@ -1442,6 +1480,7 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
     if (world > 1) {
         TK_TRY(nccl_bind());
         const std::string key(static_cast<const char*>(unique_id), 128);
+        h->comm_key = key;
         std::lock_guard<std::mutex> lock(g_mutex);
         auto it = g_comms.find(key);
         if (it == g_comms.end()) {
@@ -1470,6 +1509,10 @@ void tk_destroy(tk_handle* h) {
 }
 
 int tk_release_cache(void) {
+    {   // the exchange contexts hand their blocks back to the block cache (which takes the lock itself)
+        decltype(g_exchange) gone;
+        { std::lock_guard<std::mutex> lock(g_mutex); gone.swap(g_exchange); }
+    }
     std::lock_guard<std::mutex> lock(g_mutex);
     for (tk_resources* r : g_res_free) {
         cudaSetDevice(r->device);
