@@ -232,8 +232,8 @@ using namespace tk;
 // in particular) costs far more than a solve, so destroyed handles park the bundle in a process-level free list.
 struct tk_resources {
     int device = 0;
-    cudaStream_t s_main = nullptr, s_asm = nullptr, s_eig[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t step_ev[8], eig_ev[8], asm_ev[8], seg_ev[4], join_ev[5], ev_fork, ev_solve[2], ev_region;
+    cudaStream_t s_main = nullptr, s_asm = nullptr, s_eig[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t step_ev[8], eig_ev[8], asm_ev[8], seg_ev[4], join_ev[10], ev_fork, ev_solve[2], ev_region;
     SolveCtl* hctl = nullptr;           // pinned + mapped: tolerance/epoch in, exit status out
     SolveCtl* hctl_dev = nullptr;       // the same block as the device sees it
     cudaStream_t s_copy = nullptr;      // device -> host copies of the solution, overlapped with its computation
@@ -306,8 +306,10 @@ struct tk_handle {
     cudaStream_t stream2 = nullptr;   // CP assembly + residual (3)(4): runs behind the Krylov steps, concurrently
     // eigensolver (2): eig(k) only needs step k, so consecutive k run concurrently on NEIG round-robin streams
     // (one SM each) and overlap the Krylov steps and the assembly of earlier iterations
-    static constexpr int NEIG = 4, NBUF = 8;
-    cudaStream_t stream3[NEIG] = {nullptr, nullptr, nullptr, nullptr};
+    // (as many as the ring is deep: at k ~ 256 one bisection eigensolve takes ~1 ms on its one SM, and with few short
+    // modes -- config 2 -- the solve is bound by how many of them are in flight: 137 ms of eigensolves per 43 ms solve)
+    static constexpr int NEIG = 8, NBUF = 8;
+    cudaStream_t stream3[NEIG] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // Dependencies between the streams: one event per kind and iteration (ring of 8), valid inside the segment that
     // recorded it -- segments fork from and join into `stream`, so anything older is already complete
     struct EvSlot { cudaEvent_t ev = nullptr; int k = -1, seg = -1; };
@@ -708,8 +710,9 @@ static int launch_ttr(tk_handle* h, int k) {
 // Gram row of the newest column for `nmodes` modes starting at local mode `base`
 // Gram row of the newest column for `nmodes` modes starting at local mode `base`, followed (same launch, last CTA of
 // each mode) by the monitor: monitor = 0 plain bookkeeping, 1 = with the LanczosReorth MGS fallback.
-static int launch_gram(tk_handle* h, int ncols, int base, int nmodes, int monitor) {
+static int launch_gram(tk_handle* h, int ncols, int base, int nmodes, int monitor, cudaStream_t st = nullptr) {
     if (nmodes <= 0) return 0;
+    if (!st) st = h->stream;
     const int threads = env_int("TK_GRAM_THREADS", 256) == 512 ? 512 : 256, nwarp = threads / 32;
     // warps per column: long columns are cut into segments so all warps of a CTA stream the same amount
     int wpc = h->n >= 8192 ? 8 : h->n >= 4096 ? 4 : h->n >= 2048 ? 2 : 1;
@@ -742,11 +745,11 @@ static int launch_gram(tk_handle* h, int ncols, int base, int nmodes, int monito
     }
     const double bytes = 8.0 * (double)h->n * (double)ncols * nmodes;
     const int U = env_int("TK_GRAM_U", 4);
-    TimedScope ts(h, TM_GRAM, bytes, h->stream);
+    TimedScope ts(h, TM_GRAM, bytes, st);
 #define TK_GRAM_LAUNCH(UU, TT)                                                                                   \
     do {                                                                                                         \
         TK_TRY(allow_smem(gram_row_kernel<UU, TT>, smem));                                                       \
-        gram_row_kernel<UU, TT><<<dim3(nchunks, nmodes), TT, smem, h->stream>>>(h->kp(), ncols, cpc, base,       \
+        gram_row_kernel<UU, TT><<<dim3(nchunks, nmodes), TT, smem, st>>>(h->kp(), ncols, cpc, base,       \
                                                                                 w_smem ? 1 : 0, wpc, monitor,    \
                                                                                 h->tickets.p, h->vscratch.p);    \
     } while (0)
@@ -823,16 +826,20 @@ static int launch_arnoldi(tk_handle* h, int k) {
 }
 
 // orthonormalize!(decomp, k) for every local mode + update_rhs!   (orthogonal_bases.jl:162-180, utils.jl:466-476)
-static int enqueue_step_bases(tk_handle* h, int k) {
+// TensorLanczosReorth needs the Gram row of every mode before the next step (the monitor may replace the new column).
+// The other variants only keep the orthogonality history of mode 1 (tensor_krylov_method.jl:103): that one-mode row
+// is pure latency (18 us per launch), so inside tk_solve it runs on the residual stream ahead of the assembly
+// (history_row_inline = false -> enqueue_chain) instead of sitting between two steps of the Krylov stream.
+static int enqueue_step_bases(tk_handle* h, int k, bool history_row_inline = true) {
     const int mode0 = (h->first == 0 && h->dl > 0) ? 1 : 0;
     if (h->variant == TK_ARNOLDI) {
         TK_TRY(launch_arnoldi(h, k));
-        TK_TRY(launch_gram(h, k + 1, 0, mode0, 0));
+        if (history_row_inline) TK_TRY(launch_gram(h, k + 1, 0, mode0, 0));
     } else {
         TK_TRY(launch_ttr(h, k));
         if (h->variant == TK_LANCZOS_REORTH) {
             TK_TRY(launch_gram(h, k + 1, 0, h->dk, 1));
-        } else {
+        } else if (history_row_inline) {
             TK_TRY(launch_gram(h, k + 1, 0, mode0, 0));
         }
     }
@@ -1261,6 +1268,11 @@ static int slot_wait(tk_handle* h, tk_handle::EvSlot* ring, int k, cudaStream_t 
 // eigensolve -> CP assembly -> residual estimate of iteration k on the side streams
 static int enqueue_chain(tk_handle* h, int k) {
     cudaStream_t es = h->stream3[k % tk_handle::NEIG];
+    if (h->variant != TK_LANCZOS_REORTH && h->first == 0 && h->dl > 0) {
+        // orthogonality history of mode 1: rows follow each other on this stream (S is a running sum), combine(k) reads it
+        TK_TRY(slot_wait(h, h->step_slot, k, h->stream2));
+        TK_TRY(launch_gram(h, k + 1, 0, 1, 0, h->stream2));
+    }
     TK_TRY(slot_wait(h, h->step_slot, k, es));                             // needs the Krylov step k
     if (k - h->ring_depth >= 2) TK_TRY(slot_wait(h, h->asm_slot, k - h->ring_depth, es));   // its ring buffer is free
     TK_TRY(enqueue_eig(h, k));
@@ -1293,7 +1305,7 @@ static int enqueue_segment(tk_handle* h, int idx) {
     for (auto st : side) TK_CUDA(cudaStreamWaitEvent(st, h->res->ev_fork, 0));
     for (int k = sg.c0; k <= sg.c1 && k < sg.k0; ++k) TK_TRY(enqueue_chain(h, k));      // deferred by the last segment
     for (int k = sg.k0; k <= sg.k1; ++k) {
-        TK_TRY(enqueue_step_bases(h, k));
+        TK_TRY(enqueue_step_bases(h, k, false));
         TK_TRY(slot_record(h, h->step_slot, k, h->stream));
         if (k >= sg.c0 && k <= sg.c1) TK_TRY(enqueue_chain(h, k));
     }
