@@ -826,20 +826,16 @@ static int launch_arnoldi(tk_handle* h, int k) {
 }
 
 // orthonormalize!(decomp, k) for every local mode + update_rhs!   (orthogonal_bases.jl:162-180, utils.jl:466-476)
-// TensorLanczosReorth needs the Gram row of every mode before the next step (the monitor may replace the new column).
-// The other variants only keep the orthogonality history of mode 1 (tensor_krylov_method.jl:103): that one-mode row
-// is pure latency (18 us per launch), so inside tk_solve it runs on the residual stream ahead of the assembly
-// (history_row_inline = false -> enqueue_chain) instead of sitting between two steps of the Krylov stream.
-static int enqueue_step_bases(tk_handle* h, int k, bool history_row_inline = true) {
+static int enqueue_step_bases(tk_handle* h, int k) {
     const int mode0 = (h->first == 0 && h->dl > 0) ? 1 : 0;
     if (h->variant == TK_ARNOLDI) {
         TK_TRY(launch_arnoldi(h, k));
-        if (history_row_inline) TK_TRY(launch_gram(h, k + 1, 0, mode0, 0));
+        TK_TRY(launch_gram(h, k + 1, 0, mode0, 0));
     } else {
         TK_TRY(launch_ttr(h, k));
         if (h->variant == TK_LANCZOS_REORTH) {
             TK_TRY(launch_gram(h, k + 1, 0, h->dk, 1));
-        } else if (history_row_inline) {
+        } else {
             TK_TRY(launch_gram(h, k + 1, 0, mode0, 0));
         }
     }
@@ -1268,11 +1264,7 @@ static int slot_wait(tk_handle* h, tk_handle::EvSlot* ring, int k, cudaStream_t 
 // eigensolve -> CP assembly -> residual estimate of iteration k on the side streams
 static int enqueue_chain(tk_handle* h, int k) {
     cudaStream_t es = h->stream3[k % tk_handle::NEIG];
-    if (h->variant != TK_LANCZOS_REORTH && h->first == 0 && h->dl > 0) {
-        // orthogonality history of mode 1: rows follow each other on this stream (S is a running sum), combine(k) reads it
-        TK_TRY(slot_wait(h, h->step_slot, k, h->stream2));
-        TK_TRY(launch_gram(h, k + 1, 0, 1, 0, h->stream2));
-    }
+
     TK_TRY(slot_wait(h, h->step_slot, k, es));                             // needs the Krylov step k
     if (k - h->ring_depth >= 2) TK_TRY(slot_wait(h, h->asm_slot, k - h->ring_depth, es));   // its ring buffer is free
     TK_TRY(enqueue_eig(h, k));
@@ -1305,7 +1297,7 @@ static int enqueue_segment(tk_handle* h, int idx) {
     for (auto st : side) TK_CUDA(cudaStreamWaitEvent(st, h->res->ev_fork, 0));
     for (int k = sg.c0; k <= sg.c1 && k < sg.k0; ++k) TK_TRY(enqueue_chain(h, k));      // deferred by the last segment
     for (int k = sg.k0; k <= sg.k1; ++k) {
-        TK_TRY(enqueue_step_bases(h, k, false));
+        TK_TRY(enqueue_step_bases(h, k));
         TK_TRY(slot_record(h, h->step_slot, k, h->stream));
         if (k >= sg.c0 && k <= sg.c1) TK_TRY(enqueue_chain(h, k));
     }
@@ -1452,10 +1444,12 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
     tk_resources* r = h->res;
     h->stream = r->s_main;
     h->stream2 = env_int("TK_SINGLE_STREAM", 0) ? h->stream : r->s_asm;
+    // eigensolver streams: 8 for the bisection kernel (one CTA per problem), 4 for the dense exponentials (clusters of
+    // CTAs per term: more of them in flight only take SMs from the Arnoldi step -- measured at C4)
+    const int neig = env_int("TK_EIG_STREAMS", h->use_expm ? 4 : tk_handle::NEIG);
     for (int i = 0; i < tk_handle::NEIG; ++i) {
         if (env_int("TK_SINGLE_STREAM", 0) || env_int("TK_TWO_STREAMS", 0)) h->stream3[i] = h->stream2;
-        else if (i >= env_int("TK_EIG_STREAMS", tk_handle::NEIG)) h->stream3[i] = r->s_eig[0];
-        else h->stream3[i] = r->s_eig[i];
+        else h->stream3[i] = r->s_eig[i % std::max(1, std::min(neig, (int)tk_handle::NEIG))];
     }
     for (int i = 0; i < 8; ++i) {
         h->step_slot[i].ev = r->step_ev[i]; h->eigdone_slot[i].ev = r->eig_ev[i]; h->asm_slot[i].ev = r->asm_ev[i];
