@@ -1,10 +1,14 @@
 // tk_compress.cuh -- kernels (2) (3) (4): compressed solve and residual estimate.
 //
-//   tridiag_eig_kernel    H_k = Q diag(theta) Q'            replaces the t dense exp(gamma*Symmetric(H)) calls (utils.jl:509-511)
+//   tridiag_eig_bisect_kernel / tridiag_eig_kernel   H_k = Q diag(theta) Q'   replaces the t dense
+//                         exp(gamma*Symmetric(H)) calls (utils.jl:509-511); bisection + twisted factorisation, QL fallback
 //   assemble_cp_kernel    Y_s[:,j] = Q exp(gamma_j theta) Q' b~_s   (tensor_krylov_method.jl:10-34, utils.jl:513-521)
-//   gram_blocks_kernel    Z_s = H_s Y_s, Y'Y, Y'Z, Z'Z, ||b~_s||^2  (utils.jl:186-204, 229-253, 285-288)
+//   gram_blocks_kernel    Z_s = H_s Y_s, Y'Y, Y'Z, Z'Z, ||b~_s||^2  (utils.jl:186-204, 229-253, 285-288);
+//                         gram_z_kernel / gram_e_kernel: the same over many CTAs per mode (few modes, many terms)
 //   combine_chunk_kernel  product over modes in R[e,h]/(e^2,h^2)    (MVnorm utils.jl:280-324, boundary term :428-437,
-//   finalize_kernel       tensorinnerprod :332-369, r_comp :393, status :395 and tensor_krylov_method.jl:99-118)
+//                         tensorinnerprod :332-369); its last CTA exchanges the merged partial with the peer GPUs and runs
+//   finalize_body         r_comp :393, status :395 and tensor_krylov_method.jl:99-118  (finalize_kernel: NCCL fallback only)
+//   basis_mul_all_kernel  x.fmat[s] = V_s[:,1:k] Y_s for all modes in one launch   (basis_tensor_mul!, utils.jl:478-488)
 #pragma once
 #include "tk_device.cuh"
 

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256) expm_fused_kernel(ExpmParams p, double f0
                                                          double f15, double f16) {
     constexpr int CL = TILES * TILES;
     if (CL > 1) {
-        // The status word can flip (finalize_kernel, another stream) while this launch is starting.  The CTAs of a
+        // The status word can flip (finalize_body, another stream) while this launch is starting.  The CTAs of a
         // cluster meet at cluster barriers, so they must all take the same run/skip decision: CTA 0 of the cluster
         // reads the word and the others take its copy through distributed shared memory.
         __shared__ int st_sh;

@@ -1,11 +1,13 @@
 // tk_krylov.cuh -- kernel family (1): one launch advances the Krylov basis of every mode.
 //
+//   reset_kernel          status words, ConvergenceData = ones, control words (start of a solve)
 //   init_basis_kernel     V[:,1] = b/||b||, b~[1]                (decompositions.jl:112-118, utils.jl:456-464)
 //   lanczos_ttr_kernel    3-term recurrence step                (orthogonal_bases.jl:39-67)
 //   lanczos_ttr_bulk_kernel   the same step for banded operators, inputs fetched by cp.async.bulk (TMA)
 //   gram_row_kernel       g_j = v_j . v_{k+1}, j = 1..k+1       (the only NEW row of V'V; orthogonal_bases.jl:119,250-257)
 //   monitor_body          loss test + MGS fallback, run by the last gram_row CTA of a mode (orthogonal_bases.jl:119-131)
-//   arnoldi_mgs_kernel    two-pass modified Gram-Schmidt step   (orthogonal_bases.jl:15-37)
+//   arnoldi_bgs_kernel    two-sweep Gram-Schmidt step, 4 columns per reduction round (orthogonal_bases.jl:15-37)
+//   arnoldi_mgs_reg_kernel / arnoldi_mgs_kernel   the same step in strict MGS order (long modes)
 #pragma once
 #include "tk_device.cuh"
 
@@ -71,7 +73,7 @@ __global__ void __launch_bounds__(256) reset_kernel(ResetParams r) {
 //   v_{k+1} = v^ / beta (zeros if beta == 0);  H[k+1,k] = H[k,k+1] = beta;  b~[k+1] = v_{k+1}.b = (v^.b)/beta
 // Algorithmic HBM bytes per mode: (ndiag + 4) * 8 * n  (diagonals, v_k, v_{k-1}, b read; v_{k+1} written).
 // ------------------------------------------------------------------------------------------
-// The status word is flipped by finalize_kernel on another stream while 3-term steps of later iterations are in
+// The status word is flipped by finalize_body (the last CTA of the combine kernel) on another stream while 3-term steps of later iterations are in
 // flight.  The CTAs of a cluster exchange partial sums through each other's shared memory, so all of them must take
 // the same run/skip decision: they read a snapshot that only the 3-term kernels themselves write (launch k reads
 // slot k&1 and refreshes slot (k+1)&1 for the next launch on the same stream), never the live word.
