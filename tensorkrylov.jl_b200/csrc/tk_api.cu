@@ -25,6 +25,8 @@
 #include <thread>
 #include <vector>
 
+extern "C" char** environ;
+
 #include "../../include/tensorkrylov_b200.h"
 #include "tk_compress.cuh"
 #include "tk_expm.cuh"
@@ -121,8 +123,10 @@ static void pool_trim() {
     g_pool_bytes = 0;
 }
 
+static void evict_parked_handles();   // parked solvers give their blocks back to the cache (defined below)
+
 static cudaError_t pool_alloc(void** out, size_t bytes) {
-    std::lock_guard<std::mutex> lock(g_mutex);
+    std::unique_lock<std::mutex> lock(g_mutex);
     int dev = 0;
     cudaGetDevice(&dev);
     auto it = g_pool.find(std::make_pair(dev, bytes));
@@ -135,6 +139,9 @@ static cudaError_t pool_alloc(void** out, size_t bytes) {
     cudaError_t e = cudaMalloc(out, bytes);
     if (e == cudaErrorMemoryAllocation) {
         cudaGetLastError();
+        lock.unlock();
+        evict_parked_handles();
+        lock.lock();
         pool_trim();
         e = cudaMalloc(out, bytes);
     }
@@ -329,8 +336,9 @@ struct tk_handle {
         long long launches = 0;
     };
     std::vector<Segment> segs;
-    unsigned long long cfg_epoch = 1;    // bumped when anything baked into recorded launches changes
-    unsigned long long last_solve_epoch = 0;
+    unsigned long long sig = 0;          // signature of everything recorded launches carry as arguments (prepare)
+    unsigned long long last_solve_sig = 0;
+    std::string shape_key;               // tk_create arguments: a parked handle is revived by an identical tk_create
     long long solve_count = 0;
     SolveCtl* hctl = nullptr;            // pinned (host view)
     SolveCtl* hctl_dev = nullptr;        // pinned (device view)
@@ -401,7 +409,20 @@ struct tk_handle {
     }
 };
 
+// Solvers released by tk_destroy are parked whole (state buffers, workspaces, recorded graphs, streams) and revived by
+// a tk_create with identical arguments: the reference's calling convention builds its whole state per solve
+// (decompositions.jl:127-174), and a drop-in caller that does the same should not pay allocation, workspace set-up and
+// graph recording every time.  Inputs are NOT kept: a revived handle must be fed operators, right-hand sides and the
+// schedule like a new one.  TK_HANDLE_CACHE = number of parked handles (default 2, 0 = off).
+static std::vector<tk_handle*> g_parked;
+
 namespace tk {
+
+static void evict_parked_handles() {
+    std::vector<tk_handle*> gone;
+    { std::lock_guard<std::mutex> lock(g_mutex); gone.swap(g_parked); }
+    for (tk_handle* q : gone) delete q;        // blocks go back to the cache (pool_free takes the lock itself)
+}
 
 // developer knobs for kernel tuning experiments (unset in production)
 static int env_int(const char* name, int dflt) {
@@ -1167,8 +1188,44 @@ static int setup_peer_exchange(tk_handle* h) {
     return 0;
 }
 
+// Everything a recorded segment carries as a launch argument or used to choose a kernel: device pointers, workspace
+// strides, operator structure, the schedule (term counts, offsets, lambda_min, coefficients) and the TK_* knobs.  A
+// recorded graph is replayed only under the signature it was recorded with.
+static unsigned long long config_signature(const tk_handle* h) {
+    unsigned long long x = 1469598103934665603ULL;
+    auto mix = [&](const void* p, size_t nbytes) {
+        const unsigned char* c = static_cast<const unsigned char*>(p);
+        for (size_t i = 0; i < nbytes; ++i) { x ^= c[i]; x *= 1099511628211ULL; }
+    };
+    auto ptr = [&](const void* p) { mix(&p, sizeof(p)); };
+    ptr(h->V.p); ptr(h->b.p); ptr(h->T.p); ptr(h->Hd.p); ptr(h->bt.p); ptr(h->g.p); ptr(h->S.p); ptr(h->orthS.p);
+    ptr(h->bnorm2.p); ptr(h->vscratch.p); ptr(h->fallbacks.p); ptr(h->mode_op_d.p); ptr(h->status_d.p);
+    ptr(h->term_k_d.p); ptr(h->eigfail_d.p); ptr(h->niter_d.p); ptr(h->ops_d.p); ptr(h->alpha_d.p); ptr(h->omega_d.p);
+    ptr(h->theta.p); ptr(h->Q.p); ptr(h->Y.p); ptr(h->Z.p); ptr(h->E.p); ptr(h->bbm.p); ptr(h->partials.p);
+    ptr(h->gathered.p); ptr(h->relres_d.p); ptr(h->projres_d.p); ptr(h->orth_d.p); ptr(h->detail_d.p);
+    ptr(h->eig_scratch.p); ptr(h->eig_need.p); ptr(h->ticket_d.p); ptr(h->tickets.p); ptr(h->merged.p);
+    ptr(h->exW.p); ptr(h->ex_nsq.p); ptr(h->ex_where.p); ptr(h->cls_mode_d.p); ptr(h->ctl_d.p); ptr(h->hctl_dev);
+    mix(&h->px, sizeof(h->px));
+    const long long ints[] = {h->px_ready, h->ring_depth, h->ldq, h->ystride, h->estride, h->pstride_max, h->ex_ld, h->tmax};
+    mix(ints, sizeof(ints));
+    for (const auto& op : h->ops) {
+        const long long m[] = {op->type, op->ndiag, op->ld, op->nnz, op->constd};
+        mix(m, sizeof(m)); mix(op->offs, sizeof(op->offs)); mix(op->cval, sizeof(op->cval)); mix(&op->norm_bound, 8);
+    }
+    mix(h->mode_op.data(), h->mode_op.size() * sizeof(int));
+    for (size_t k = 2; k < h->sched.size(); ++k) {
+        const SchedEntry& se = h->sched[k];
+        const long long m[] = {se.set, se.t, (long long)se.off};
+        mix(m, sizeof(m)); mix(&se.lambda_min, 8);
+    }
+    mix(h->alpha_pool.data(), h->alpha_pool.size() * 8);
+    mix(h->omega_pool.data(), h->omega_pool.size() * 8);
+    for (char** e = environ; e && *e; ++e)
+        if (std::strncmp(*e, "TK_", 3) == 0) mix(*e, std::strlen(*e));
+    return x ? x : 1;
+}
+
 static int prepare(tk_handle* h, bool with_schedule) {
-    const bool od = h->ops_dirty, sd = h->sched_dirty, wr = h->work_ready;
     TK_TRY(upload_ops(h));
     for (int s = 0; s < h->dk; ++s)
         if (!h->rhs_set[s]) return set_error(TK_ESTATE, "right-hand side of mode %d not set", s < h->dl ? h->first + s : 0);
@@ -1176,7 +1233,6 @@ static int prepare(tk_handle* h, bool with_schedule) {
         TK_TRY(upload_schedule(h));
         TK_TRY(alloc_work(h));
     }
-    if (od || (with_schedule && (sd || !wr))) h->cfg_epoch++;
     // working vector of the MGS step when it does not fit in shared memory
     const size_t need_gram = ((size_t)32 * GRAM_PSTRIDE + ((h->ncol + 1) & ~1) + (size_t)h->n) * 8;
     const size_t need_mgs = ((size_t)h->ncol + (size_t)h->n) * 8;
@@ -1185,8 +1241,8 @@ static int prepare(tk_handle* h, bool with_schedule) {
     const bool gram_l1 = wsm_env >= 0 ? wsm_env == 0 : h->dk >= 64;
     if ((need_gram > smem_limit(h) || need_mgs > smem_limit(h) || gram_l1) && !h->vscratch.p) {
         TK_TRY(h->vscratch.alloc((size_t)h->dk * h->ldv));
-        h->cfg_epoch++;
     }
+    h->sig = config_signature(h);
     return 0;
 }
 
@@ -1335,7 +1391,7 @@ static int launch_segment(tk_handle* h, int idx, bool graph) {
     tk_handle::Segment& sg = h->segs[idx];
     NvtxRange range("tk segment");
     if (!graph) return enqueue_segment(h, idx);
-    if (!sg.exec || sg.epoch != h->cfg_epoch) {
+    if (!sg.exec || sg.epoch != h->sig) {
         NvtxRange rec("tk record graph");
         const auto t0 = std::chrono::steady_clock::now();
         if (sg.exec) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; }
@@ -1351,7 +1407,7 @@ static int launch_segment(tk_handle* h, int idx, bool graph) {
         const cudaError_t ei = cudaGraphInstantiate(&sg.exec, g, 0);
         cudaGraphDestroy(g);
         if (ei != cudaSuccess) { sg.exec = nullptr; return set_error(TK_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ei)); }
-        sg.epoch = h->cfg_epoch;
+        sg.epoch = h->sig;
         h->graph_build_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
     TK_CUDA(cudaGraphLaunch(sg.exec, h->stream));
@@ -1416,7 +1472,39 @@ int tk_create(tk_handle** out, int32_t d, const int64_t* n, int32_t nmax, int32_
     if (device < 0 || device >= ndev) return set_error(TK_ECUDA, "CUDA device %d not available (%d visible)", device, ndev);
     TK_CUDA(cudaSetDevice(device));
 
+    char keybuf[256];
+    snprintf(keybuf, sizeof(keybuf), "%d|%lld|%d|%d|%d|%d|%d|%d|%d|%d|", d, (long long)n[0], nmax, instance, matrixclass, variant,
+             flags, device, rank, world);
+    std::string shape_key(keybuf);
+    if (world > 1) shape_key.append(static_cast<const char*>(unique_id), 128);
+    for (char** e = environ; e && *e; ++e)       // developer knobs are read when a handle and its workspaces are built
+        if (std::strncmp(*e, "TK_", 3) == 0) { shape_key.push_back('|'); shape_key.append(*e); }
+    {
+        tk_handle* found = nullptr;
+        {
+            std::lock_guard<std::mutex> lock(g_mutex);
+            for (size_t i = g_parked.size(); i-- > 0;)
+                if (g_parked[i]->shape_key == shape_key) { found = g_parked[i]; g_parked.erase(g_parked.begin() + i); break; }
+        }
+        if (found) {       // revive: same buffers and recorded graphs, no inputs
+            found->ops.clear();
+            found->mode_op.assign(found->mode_op.size(), -1);
+            found->rhs_set.assign(found->rhs_set.size(), 0);
+            found->ops_dirty = true;
+            found->sched.assign(nmax + 1, SchedEntry());
+            found->alpha_pool.clear(); found->omega_pool.clear();
+            found->sched_dirty = true;
+            found->a1_lead.clear();
+            found->begun = false;
+            found->last_k = 0; found->last_t = 0; found->last_tld = 0;
+            found->timed.clear(); found->ev_used = 0; found->launches = 0;
+            *out = found;
+            return 0;
+        }
+    }
+
     std::unique_ptr<tk_handle> h(new tk_handle());
+    h->shape_key = shape_key;
     h->d = d; h->n = (int)n[0]; h->nmax = nmax; h->ncol = nmax + 1;
     h->instance = instance; h->matrixclass = matrixclass; h->variant = variant; h->flags = flags;
     h->device = device; h->rank = rank; h->world = world;
@@ -1511,10 +1599,20 @@ void tk_destroy(tk_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->stream2) cudaStreamSynchronize(h->stream2);
     for (auto st : h->stream3) if (st) cudaStreamSynchronize(st);
-    delete h;                           // parks streams, events and the pinned ring for the next handle
+    const int cap = env_int("TK_HANDLE_CACHE", 2);
+    tk_handle* evicted = nullptr;
+    if (cap > 0 && cudaGetLastError() == cudaSuccess) {
+        std::lock_guard<std::mutex> lock(g_mutex);
+        if ((int)g_parked.size() >= cap) { evicted = g_parked.front(); g_parked.erase(g_parked.begin()); }
+        g_parked.push_back(h);
+        h = nullptr;
+    }
+    delete evicted;
+    delete h;                           // parks streams, events and the pinned control block for the next handle
 }
 
 int tk_release_cache(void) {
+    evict_parked_handles();
     {   // the exchange contexts hand their blocks back to the block cache (which takes the lock itself)
         decltype(g_exchange) gone;
         { std::lock_guard<std::mutex> lock(g_mutex); gone.swap(g_exchange); }
@@ -1884,17 +1982,18 @@ int tk_solve(tk_handle* h, double tol, int32_t* status, int64_t* niter, int32_t*
     if (!h) return set_error(TK_EINVAL, "null handle");
     NvtxRange range("tk_solve");
     TK_CUDA(cudaSetDevice(h->device));
-    const unsigned long long epoch_before = h->cfg_epoch;
     TK_TRY(prepare(h, true));
     plan_segments(h);
     // Enqueue mode.  Kernel timing needs events between the launches, so it takes the direct path.  Otherwise the
     // segments are recorded as CUDA graphs the second time a handle solves with an unchanged configuration (a
     // one-shot solve would pay for the recording without using it twice); TK_GRAPH = 0 never, 2 from the first solve.
+    // "Handle" includes a parked one that an identical tk_create revived: a caller that builds a solver per solve
+    // (the reference's calling convention) replays graphs from its third solve on.
     const int gmode = env_int("TK_GRAPH", 1);
     const bool timed = (h->flags & (TK_FLAG_TIME_KERNELS | TK_FLAG_TIME_ALL)) != 0;
-    const bool repeat = h->last_solve_epoch == h->cfg_epoch && epoch_before == h->cfg_epoch;
+    const bool repeat = h->last_solve_sig == h->sig;
     const bool graph = !timed && (gmode >= 2 || (gmode == 1 && repeat));
-    h->last_solve_epoch = h->cfg_epoch;
+    h->last_solve_sig = h->sig;
     arm_solve(h, tol);
     const bool fixed = (h->flags & TK_FLAG_FIXED_ITERATIONS) != 0;
     TK_CUDA(cudaEventRecord(h->ev_solve[0], h->stream));

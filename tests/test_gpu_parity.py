@@ -708,3 +708,49 @@ def test_bulk_copy_ttr_kernel_is_bit_identical_to_the_plain_kernel(tk, orc, gpu,
         assert np.array_equal(Ha, Hb)
         assert np.array_equal(Va, Vb)
         assert np.array_equal(ba, bb)
+
+
+def test_parked_handle_is_revived_clean_and_replays_graphs(tk, orc, tables, gpu, monkeypatch):
+    """tk_destroy parks a solver whole; a tk_create with identical arguments revives it.  A revived handle has NO
+    inputs (it must be fed like a new one), gives bit-identical results, replays the recorded CUDA graphs when the
+    inputs are the same -- a caller that builds a solver per solve, like the reference does -- and re-records them
+    when an input that is baked into the launches changes."""
+    d, n, nmax, tol = 6, 500, 24, 1e-8
+    b = np.random.default_rng(3).random(n)
+    b /= np.linalg.norm(b)
+    A = tk.assemble_matrix(n, tk.Laplace)
+    lib, check = tk._capi.lib, tk._capi.check
+    check(lib.tk_release_cache())
+
+    def one(A_, graphs_expected=None, feed=True):
+        s = tk.Solver(d, n, nmax, tk.SymInstance, tk.Laplace, tk.TensorLanczosReorth,
+                      flags=tk.TK_FLAG_REFERENCE_H1 | tk.TK_FLAG_FIXED_ITERATIONS)
+        try:
+            if not feed:
+                with pytest.raises(tk.TKError):
+                    s.solve(tol)
+                return None
+            s.set_operators([A_] * d)
+            s.set_rhs([b] * d)
+            s.set_schedule(A_, tol)
+            r = s.solve(tol)
+            if graphs_expected is not None:
+                assert (s.solve_info()["graphs_launched"] > 0) == graphs_expected
+            return r["relres"].copy(), s.get_H(0).copy()
+        finally:
+            s.close()
+
+    r1, H1 = one(A, graphs_expected=False)          # new handle: stream launches
+    r2, H2 = one(A, graphs_expected=True)           # revived, same configuration: records and replays graphs
+    r3, H3 = one(A, graphs_expected=True)           # revived again: pure replay
+    assert np.array_equal(r1, r2) and np.array_equal(r1, r3) and np.array_equal(H1, H3)
+    one(A, feed=False)                              # revived without inputs: refuses to solve
+    # a different operator of the same shape on the revived handle: same result as on a brand-new handle
+    A2 = (A * 1.5).tocsc()
+    r4, H4 = one(A2)
+    monkeypatch.setenv("TK_HANDLE_CACHE", "0")      # the environment is part of the key: this one is built from scratch
+    r5, H5 = one(A2, graphs_expected=False)
+    assert np.array_equal(r4, r5) and np.array_equal(H4, H5)
+    assert not np.array_equal(H1, H4)
+    monkeypatch.delenv("TK_HANDLE_CACHE")
+    check(lib.tk_release_cache())
