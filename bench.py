@@ -491,8 +491,9 @@ def run_b200(a):
         d2h = 3 * nmax * 8 + 64
         e2e = {"value": a.steps * (nmax - 1) / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.steps,
-               "note": "fresh handle per step: handle creation, operator/rhs/schedule upload, solve (stream launches: "
-                       "graphs are only recorded for a handle that solves twice), histories back"}
+               "note": "a solver created, fed and destroyed per step (the reference's calling convention): tk_create "
+                       "(revives the solver parked by the previous step, inputs cleared), operator/rhs/schedule upload, solve "
+                       "(CUDA-graph replay once the same configuration has been solved twice), histories back"}
 
     if rank != 0:
         if world > 1:
