@@ -305,6 +305,7 @@ struct tk_handle {
                          // reference's H_1-for-all-modes rule is on and another rank owns mode 0
     int eig_slot = 0;    // local slot whose T feeds class 0 under TK_FLAG_REFERENCE_H1
     int instance = 0, matrixclass = 0, variant = 0, flags = 0, device = 0, rank = 0, world = 1, sm_count = 148;
+    bool gram_does_bt = false;     // the last 3-term launch left b~[k+1] to the Gram-row kernel that follows it
     long long ldv = 0;
     int per_mode = 0, ncls = 1;
     bool use_expm = false;   // compressed solve through the dense exponential (NonSymInstance, and the EigValMat class)
@@ -616,9 +617,9 @@ static int launch_ttr_t(tk_handle* h, int k, int threads, size_t smem) {
     return 0;
 }
 
-template <int CPM, int ND, bool CONSTD, int RPT>
+template <int CPM, int ND, bool CONSTD, int RPT, bool WITHB>
 static int launch_ttr_bulk_t(tk_handle* h, int k, int threads, size_t smem) {
-    auto kernel = lanczos_ttr_bulk_kernel<CPM, ND, CONSTD, RPT>;
+    auto kernel = lanczos_ttr_bulk_kernel<CPM, ND, CONSTD, RPT, WITHB>;
     TK_TRY(allow_smem(kernel, smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(h->dk * CPM);
@@ -661,18 +662,26 @@ static int launch_ttr_bulk(tk_handle* h, int k, int nd) {
     if (cpm != 1 && cpm != 2 && cpm != 4 && cpm != 8) return 1;
     const int chunk = (((h->n + cpm - 1) / cpm) + 1) & ~1;
     if ((long long)(cpm - 1) * chunk >= h->n || chunk < 64) return 1;      // every CTA of a cluster owns rows
-    const size_t smem = ((size_t)3 * chunk + 2 * TTR_HALO) * 8;
+    // with full orthogonalisation the Gram-row kernel that follows supplies b~[k+1] (TK_TTR_NOB = 0: compute it here)
+    const bool withb = !(h->variant == TK_LANCZOS_REORTH && env_int("TK_TTR_NOB", 1));
+    const size_t smem = ((size_t)(withb ? 3 : 2) * chunk + 2 * TTR_HALO) * 8;
     if (smem > smem_limit(h)) return 1;
     // every thread keeps TTR_RPT rows of its slice in registers (5 and 20 rows per thread measured slower)
     int threads = std::max(64, (((chunk + TTR_RPT - 1) / TTR_RPT) + 31) & ~31);
     if (env_int("TK_TTR_THREADS", 0)) threads = std::max(threads, env_int("TK_TTR_THREADS", 0));
     if (threads > 512) return 1;
+    h->gram_does_bt = !withb;
+#define TK_BULK_ND(C, N)                                                                                 \
+    do {                                                                                                 \
+        if (withb) return constd ? launch_ttr_bulk_t<C, N, true, TTR_RPT, true>(h, k, threads, smem)     \
+                                 : launch_ttr_bulk_t<C, N, false, TTR_RPT, true>(h, k, threads, smem);   \
+        return constd ? launch_ttr_bulk_t<C, N, true, TTR_RPT, false>(h, k, threads, smem)               \
+                      : launch_ttr_bulk_t<C, N, false, TTR_RPT, false>(h, k, threads, smem);             \
+    } while (0)
 #define TK_BULK_CASE(C)                                                                                  \
     case C:                                                                                              \
-        if (nd == 3) return constd ? launch_ttr_bulk_t<C, 3, true, TTR_RPT>(h, k, threads, smem)         \
-                                   : launch_ttr_bulk_t<C, 3, false, TTR_RPT>(h, k, threads, smem);       \
-        return constd ? launch_ttr_bulk_t<C, 4, true, TTR_RPT>(h, k, threads, smem)                      \
-                      : launch_ttr_bulk_t<C, 4, false, TTR_RPT>(h, k, threads, smem);
+        if (nd == 3) TK_BULK_ND(C, 3);                                                                   \
+        TK_BULK_ND(C, 4);
     switch (cpm) {
         TK_BULK_CASE(1)
         TK_BULK_CASE(2)
@@ -680,12 +689,15 @@ static int launch_ttr_bulk(tk_handle* h, int k, int nd) {
         TK_BULK_CASE(8)
     }
 #undef TK_BULK_CASE
+#undef TK_BULK_ND
+    h->gram_does_bt = false;
     return 1;
 }
 
 static int launch_ttr(tk_handle* h, int k) {
     const double bytes = (op_bytes_per_row(h) + 32.0) * (double)h->n * h->dk;
     TimedScope ts(h, TM_TTR, bytes, h->stream);
+    h->gram_does_bt = false;
     // CTAs per mode (one cluster): at least 2 whenever a slice keeps >= 2048 rows (measured best on B200 at
     // n = 10^4), more when the modes alone cannot fill the machine or a slice would not fit in shared memory
     int cpm = 1;
@@ -709,6 +721,7 @@ static int launch_ttr(tk_handle* h, int k) {
     if (env_int("TK_TTR_GENERIC", 0)) nd = 0;
     {
         const int rc = launch_ttr_bulk(h, k, nd);
+        if (h->gram_does_bt) ts.bytes -= 8.0 * (double)h->n * h->dk;      // b_s is not read at all
         if (rc != 1) return rc;
     }
 #define TK_TTR_CASE(C)                                                        \
@@ -731,7 +744,8 @@ static int launch_ttr(tk_handle* h, int k) {
 // Gram row of the newest column for `nmodes` modes starting at local mode `base`
 // Gram row of the newest column for `nmodes` modes starting at local mode `base`, followed (same launch, last CTA of
 // each mode) by the monitor: monitor = 0 plain bookkeeping, 1 = with the LanczosReorth MGS fallback.
-static int launch_gram(tk_handle* h, int ncols, int base, int nmodes, int monitor, cudaStream_t st = nullptr) {
+static int launch_gram(tk_handle* h, int ncols, int base, int nmodes, int monitor, cudaStream_t st = nullptr,
+                       bool bt_from_g = false) {
     if (nmodes <= 0) return 0;
     if (!st) st = h->stream;
     const int threads = env_int("TK_GRAM_THREADS", 256) == 512 ? 512 : 256, nwarp = threads / 32;
@@ -772,7 +786,8 @@ static int launch_gram(tk_handle* h, int ncols, int base, int nmodes, int monito
         TK_TRY(allow_smem(gram_row_kernel<UU, TT>, smem));                                                       \
         gram_row_kernel<UU, TT><<<dim3(nchunks, nmodes), TT, smem, st>>>(h->kp(), ncols, cpc, base,       \
                                                                                 w_smem ? 1 : 0, wpc, monitor,    \
-                                                                                h->tickets.p, h->vscratch.p);    \
+                                                                                h->tickets.p, h->vscratch.p,     \
+                                                                                bt_from_g ? 1 : 0);              \
     } while (0)
     if (threads == 512) {
         if (U == 8) TK_GRAM_LAUNCH(8, 512); else if (U == 2) TK_GRAM_LAUNCH(2, 512); else TK_GRAM_LAUNCH(4, 512);
@@ -855,7 +870,7 @@ static int enqueue_step_bases(tk_handle* h, int k) {
     } else {
         TK_TRY(launch_ttr(h, k));
         if (h->variant == TK_LANCZOS_REORTH) {
-            TK_TRY(launch_gram(h, k + 1, 0, h->dk, 1));
+            TK_TRY(launch_gram(h, k + 1, 0, h->dk, 1, nullptr, h->gram_does_bt));
         } else {
             TK_TRY(launch_gram(h, k + 1, 0, mode0, 0));
         }

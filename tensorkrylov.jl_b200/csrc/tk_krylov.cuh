@@ -214,8 +214,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 constexpr int TTR_RPT = 10;   // rows per thread of the bulk kernel (its u / v^ slice lives in registers)
 
-template <int CPM, int ND, bool CONSTD, int RPT>
+template <int CPM, int ND, bool CONSTD, int RPT, bool WITHB>
 __global__ void __launch_bounds__(512) lanczos_ttr_bulk_kernel(KrylovParams p, int k) {
+    // WITHB = false: b~_s[k+1] = v_{k+1} . b_s is left to the Gram-row kernel that follows (it has v_{k+1} . v_1 and
+    // v_1 = b_s / |b_s|): this kernel then moves 24 instead of 32 bytes per row and keeps two slices instead of three
+    // in shared memory (40 KB at 2 500 rows: 4 CTAs per SM instead of 3).
     // the snapshot is only consumed after the bulk loads have been issued (and have landed): its latency is off the
     // critical path, and a skipped launch merely fetches three slices it does not use
     const bool running = ttr_running(p, k);
@@ -246,11 +249,11 @@ __global__ void __launch_bounds__(512) lanczos_ttr_bulk_kernel(KrylovParams p, i
         const int he = (int)min((long long)((hi + 1) & ~1), p.ldv);
         const int g0 = max(lo - TTR_HALO, 0), g1 = (int)min((long long)he + TTR_HALO, p.ldv);
         const uint32_t bytes_v = (uint32_t)(g1 - g0) * 8u, bytes_s = (uint32_t)(he - lo) * 8u;
-        const uint32_t total = bytes_v + bytes_s * (vkm1 ? 2u : 1u);
+        const uint32_t total = bytes_v + bytes_s * ((vkm1 ? 1u : 0u) + (WITHB ? 1u : 0u));
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(&bar)), "r"(total) : "memory");
         bulk_load(smem + (g0 - lo + TTR_HALO), vk + g0, bytes_v, &bar);
         if (vkm1) bulk_load(smem + chunk + 2 * TTR_HALO, vkm1 + lo, bytes_s, &bar);
-        bulk_load(smem + 2 * chunk + 2 * TTR_HALO, b + lo, bytes_s, &bar);
+        if (WITHB) bulk_load(smem + 2 * chunk + 2 * TTR_HALO, b + lo, bytes_s, &bar);
     }
     // A CTA may only touch a peer's shared memory once that peer has started: arrive on the cluster barrier now,
     // wait for it right before the first remote store (by then every peer has long arrived: no time is spent there).
@@ -305,10 +308,11 @@ __global__ void __launch_bounds__(512) lanczos_ttr_bulk_kernel(KrylovParams p, i
             const double w = u[r] - alpha * vks[li];
             u[r] = w;
             acc = fma(w, w, acc);
-            accb = fma(w, bs[li], accb);
+            if (WITHB) accb = fma(w, bs[li], accb);
         }
     }
-    block_sum2(acc, accb, scratch);
+    if (WITHB) block_sum2(acc, accb, scratch);
+    else acc = block_sum(acc, scratch);
     double beta2 = acc, vb = accb;
     if (CPM > 1) {
         // push the two partials into every CTA of the cluster; after the barrier each CTA only reads its own
@@ -335,7 +339,7 @@ __global__ void __launch_bounds__(512) lanczos_ttr_bulk_kernel(KrylovParams p, i
         T[k - 1] = alpha;                   // H[k,k]
         T[p.ncol + (k - 1)] = beta;         // H[k+1,k]
         T[2 * p.ncol + (k - 1)] = beta;     // H[k,k+1]   update_subdiagonals!, decompositions.jl:180-186
-        p.bt[(long long)s * p.ncol + k] = btn;
+        if (WITHB) p.bt[(long long)s * p.ncol + k] = btn;
     }
 }
 
@@ -444,7 +448,10 @@ constexpr int GRAM_PSTRIDE = 16;   // partial sums per column (>= warps per colu
 template <int U, int THREADS>   // U = 16-byte loads in flight per lane and column (two columns are streamed at once)
 __global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 2 : 1)) gram_row_kernel(KrylovParams p, int ncols, int cols_per_cta, int mode_base,
                                                        int w_in_smem, int wpc, int monitor /* -1 none, 0, 1 = reorth */,
-                                                       unsigned int* tickets, double* vscratch) {
+                                                       unsigned int* tickets, double* vscratch, int bt_from_g) {
+    // bt_from_g = 1: b~_s[ncols] (1-based) = v_ncols . b_s is taken from this row's first entry: v_1 = b_s / b~_s[1]
+    // (init_basis_kernel), so v_ncols . b_s = b~_s[1] (v_ncols . v_1) up to one rounding of a quantity that is itself
+    // rounding noise (the columns are orthogonal).  The bulk 3-term kernel then never reads b_s (see there).
     // wpc = warps that share one column: every column is cut into wpc contiguous segments so all warps of the
     // CTA stream equal amounts, whatever the number of columns.
     if (!cta_running(p.status)) return;
@@ -525,6 +532,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS == 256 ? 2 : 1)) gram_row_ke
         double acc = 0.0;
         for (int sgi = 0; sgi < wpc; ++sgi) acc += part[(j - c0) * GRAM_PSTRIDE + sgi];
         g[j] = acc;
+        if (bt_from_g && j == 0) p.bt[(long long)s * p.ncol + (ncols - 1)] = acc * p.bt[(long long)s * p.ncol];
     }
     if (monitor < 0) return;
     // the CTA of this mode that finishes last folds the row into S (and runs the MGS fallback if needed)

@@ -710,6 +710,43 @@ def test_bulk_copy_ttr_kernel_is_bit_identical_to_the_plain_kernel(tk, orc, gpu,
         assert np.array_equal(ba, bb)
 
 
+@pytest.mark.parametrize("n,cpm", [(1000, 1), (4001, 2)])
+def test_rhs_projection_taken_from_the_gram_row_matches_the_direct_dot_product(tk, orc, gpu, monkeypatch, n, cpm):
+    """With full orthogonalisation the bulk 3-term kernel does not read b_s: b~_s[k+1] = v_{k+1} . b_s is
+    b~_s[1] (v_{k+1} . v_1), the first entry of the Gram row the monitor needs anyway (v_1 = b_s / |b_s|,
+    decompositions.jl:25-36).  Against the kernel that forms the dot product with b_s itself (TK_TTR_NOB = 0): the
+    bases and H are bit-identical (they never depend on b~), b~ agrees to rounding of |b_s| -- the entries beyond the
+    first are themselves rounding noise -- and the residual histories of a whole solve agree."""
+    d, nmax = 3, 30
+    rng = np.random.default_rng(n)
+    A = tk.assemble_matrix(n, tk.Laplace)
+    b = orc.normalize_rhs([rng.random(n) for _ in range(d)])
+    monkeypatch.setenv("TK_TTR_CPM", str(cpm))
+
+    def run(nob):
+        monkeypatch.setenv("TK_TTR_NOB", "1" if nob else "0")
+        s = make_solver(tk, [A] * d, b, nmax, tk.TensorLanczosReorth, tk.SymInstance, tk.Laplace)
+        s.begin()
+        for k in range(2, nmax + 1):
+            s.step_bases(k)
+        bases = [(s.get_H(m), s.get_V(m, nmax + 1), s.get_bt(m)) for m in range(d)]
+        s.close()
+        s = make_solver(tk, [A] * d, b, nmax, tk.TensorLanczosReorth, tk.SymInstance, tk.Laplace, tol=1e-8)
+        hist = s.solve(1e-8)["relres"].copy()
+        s.close()
+        return bases, hist
+
+    (ba, ha), (bb, hb) = run(True), run(False)
+    for (Ha, Va, bta), (Hb, Vb, btb) in zip(ba, bb):
+        assert np.array_equal(Ha, Hb)
+        assert np.array_equal(Va, Vb)
+        assert bta[0] == btb[0]
+        assert np.max(np.abs(bta - btb)) <= 1e-14 * abs(bta[0])
+    ok = np.isfinite(ha) & np.isfinite(hb) & (hb > 0)
+    assert np.array_equal(np.isfinite(ha), np.isfinite(hb))
+    assert np.max(np.abs(ha[ok] - hb[ok]) / hb[ok]) < 1e-9
+
+
 def test_parked_handle_is_revived_clean_and_replays_graphs(tk, orc, tables, gpu, monkeypatch):
     """tk_destroy parks a solver whole; a tk_create with identical arguments revives it.  A revived handle has NO
     inputs (it must be fed like a new one), gives bit-identical results, replays the recorded CUDA graphs when the
