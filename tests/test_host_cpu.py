@@ -376,7 +376,7 @@ def test_committed_r02_launch_list_matches_its_summary():
 def test_committed_bench_lines_carry_the_contract_keys():
     """profiles/r02_bench_n{1,2,4,8}: one JSON line each with the contract's keys, parity green at every N."""
     import json
-    for name, n in (("r02_bench_n1.json", 1), ("r02_bench_n2_2gpu_box.json", 2), ("r02_bench_n4.json", 4), ("r02_bench_n8.json", 8)):
+    for name, n in (("r02_bench_n1.json", 1), ("r02_bench_n2.json", 2), ("r02_bench_n4.json", 4), ("r02_bench_n8.json", 8)):
         d = json.load(open(os.path.join(ROOT, "profiles", name)))
         assert d["metric"] == "krylov_iters_per_s" and d["n_gpus"] == n and d["dtype"] == "f64" and d["value"] > 0
         assert d["roofline"]["bound"] == "hbm" and 0 < d["roofline"]["frac"] < 1.1 and d["gpu_launches"] > 0
