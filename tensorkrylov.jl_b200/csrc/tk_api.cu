@@ -654,7 +654,8 @@ static int launch_ttr_bulk(tk_handle* h, int k, int nd) {
         constd = constd && o.constd;
     }
     if (env_int("TK_TTR_NOCONST", 0)) constd = false;
-    // CTAs per mode: slices of <= 2560 rows (60 KB of shared memory -> 3 CTAs per SM), at least 64 rows each
+    // CTAs per mode: slices of <= 2560 rows (40 KB of shared memory -> 4 CTAs per SM; 60 KB -> 3 with the b slice),
+    // at least 64 rows each
     int cpm = 1;
     while (cpm < 8 && h->n / cpm > 2560) cpm *= 2;
     while (cpm < 8 && (long long)h->dk * cpm < 296 && h->n / (2 * cpm) >= 512) cpm *= 2;

@@ -183,8 +183,8 @@ __global__ void __launch_bounds__(512) lanczos_ttr_kernel(KrylovParams p, int k)
 
 // ------------------------------------------------------------------------------------------
 // Bulk-copy variant of the 3-term step for banded operators (DIA, every |offset| <= TTR_HALO).
-// The slices of v_k (with a halo), v_{k-1} and b a CTA needs are fetched by three cp.async.bulk copies that
-// complete on one mbarrier, so a CTA has its whole input (24 bytes per row) in flight from its first
+// The slices of v_k (with a halo), v_{k-1} and -- WITHB only -- b a CTA needs are fetched by cp.async.bulk copies that
+// complete on one mbarrier, so a CTA has its whole input (16 or 24 bytes per row) in flight from its first
 // instruction without holding registers for it; the three passes then run out of shared memory and the only
 // global traffic left in them is the diagonals (L2-resident, or none at all when every diagonal is constant:
 // CONSTD) and the store of v_{k+1}.  Same thread-to-row map and reduction order as lanczos_ttr_kernel, so for
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(512) lanczos_ttr_bulk_kernel(KrylovParams p, i
     // v_1 = b_s / |b_s|): this kernel then moves 24 instead of 32 bytes per row and keeps two slices instead of three
     // in shared memory (40 KB at 2 500 rows: 4 CTAs per SM instead of 3).
     // the snapshot is only consumed after the bulk loads have been issued (and have landed): its latency is off the
-    // critical path, and a skipped launch merely fetches three slices it does not use
+    // critical path, and a skipped launch merely fetches slices it does not use
     const bool running = ttr_running(p, k);
     extern __shared__ __align__(16) double smem[];
     __shared__ double scratch[64];
