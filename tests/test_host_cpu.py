@@ -385,3 +385,5 @@ def test_committed_bench_lines_carry_the_contract_keys():
     d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_n1.json")))
     assert d["cpu_baseline"]["kind"] == "port" and "nothing scaled" in d["cpu_baseline"]["sample"]
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["time_to_tol"]["with_solution_ms"] > d["time_to_tol"]["device_ms"]
+    # the other Lanczos variant at the same sizes rides on the default line (no Gram row over all modes: faster)
+    assert d["variants"]["TensorLanczos"]["value"] > d["value"]
